@@ -1,0 +1,1027 @@
+// b200lp.cu -- host side of libb200lp.so: the C ABI of include/b200lp.h over the sm_100a kernels.
+//
+// The pivot loop is device resident: every iteration is three launches (price -> ratio -> update) that
+// communicate through a DevState in device memory; the host replays a CUDA graph of `check_every` iterations
+// and only reads the status word back between replays (double buffered, so the GPU never waits for the host).
+// No cuBLAS, no Triton, no CPU fallback: without a CUDA device every compute entry point fails with
+// B200LP_E_CUDA.
+#include "../../include/b200lp.h"
+
+#include <cuda.h>
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "common.cuh"
+#include "kernels_batched.cuh"
+#include "kernels_build.cuh"
+#include "kernels_pick.cuh"
+#include "kernels_update.cuh"
+
+using namespace b200lp;
+
+#define B200LP_API extern "C" __attribute__((visibility("default")))
+
+// ------------------------------------------------------------------------------------------------------
+// errors
+// ------------------------------------------------------------------------------------------------------
+static thread_local std::string g_err;
+
+static int fail(int code, const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    g_err = buf;
+    return code;
+}
+
+#define CK(call)                                                                                         \
+    do {                                                                                                 \
+        cudaError_t e__ = (call);                                                                        \
+        if (e__ != cudaSuccess)                                                                          \
+            return fail(B200LP_E_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__), __FILE__, __LINE__); \
+    } while (0)
+
+#define CKR(call)               \
+    do {                        \
+        int rc__ = (call);      \
+        if (rc__) return rc__;  \
+    } while (0)
+
+// ------------------------------------------------------------------------------------------------------
+// workspace
+// ------------------------------------------------------------------------------------------------------
+template <typename T>
+struct DevBuf {
+    T* p = nullptr;
+    size_t cap = 0;  // elements
+    int ensure(size_t n) {
+        if (n <= cap) return 0;
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+        cudaError_t e = cudaMalloc(&p, n * sizeof(T));
+        if (e != cudaSuccess) return fail(B200LP_E_NOMEM, "cudaMalloc(%zu bytes): %s", n * sizeof(T), cudaGetErrorString(e));
+        cap = n;
+        return 0;
+    }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+    }
+};
+
+struct GraphKey {
+    const double* T = nullptr;
+    int64_t R = 0, C = 0, ld = 0, obj_row = -1;
+    int32_t rule = -1, variant = -1, iters = 0;
+    double eps_cost = 0, eps_pivot = 0;
+    int64_t hist_cap = 0;
+    bool operator==(const GraphKey& o) const {
+        return T == o.T && R == o.R && C == o.C && ld == o.ld && obj_row == o.obj_row && rule == o.rule &&
+               variant == o.variant && iters == o.iters && eps_cost == o.eps_cost && eps_pivot == o.eps_pivot &&
+               hist_cap == o.hist_cap;
+    }
+};
+
+struct b200lp_solver {
+    int device = 0;
+    int sm_count = 148;
+    cudaStream_t own_stream = nullptr;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_state[2] = {nullptr, nullptr};
+
+    // tableau (attached: caller owned; otherwise `own_T`)
+    double* T = nullptr;
+    DevBuf<double> own_T;
+    int64_t m = 0, n_obj = 0, R = 0, C = 0, ld = 0, n_struct = 0;
+    int32_t art_base = 0;
+
+    DevBuf<int32_t> rowlab, collab;
+    DevBuf<double> col;
+    DevBuf<Key> part_price, part_ratio;
+    DevBuf<DevState> st;
+    DevState* st_host = nullptr;  // pinned, 2 entries
+    DevBuf<int32_t> h_row, h_col, h_enter, h_leave;
+    int64_t hist_cap = 0;
+
+    // staging for solve_dense / solve_batched
+    DevBuf<double> sA, sb, sc, sx, sfun;
+    DevBuf<RowInfo> sinfo;
+    DevBuf<int8_t> sops;
+    DevBuf<int32_t> sstatus, snpiv, slog;
+
+    // TMA descriptor of the current tableau
+    CUtensorMap tmap;
+    const double* tmap_T = nullptr;
+    int64_t tmap_R = 0, tmap_C = 0, tmap_ld = 0;
+
+    cudaGraphExec_t graph = nullptr;
+    GraphKey graph_key;
+    int64_t launches = 0;
+};
+
+static int set_device(b200lp_solver* s) {
+    CK(cudaSetDevice(s->device));
+    return 0;
+}
+
+B200LP_API int b200lp_version(void) { return B200LP_VERSION; }
+B200LP_API const char* b200lp_last_error(void) { return g_err.c_str(); }
+
+B200LP_API void b200lp_default_opts(b200lp_opts* o) {
+    if (!o) return;
+    o->rule = B200LP_RULE_DANTZIG;
+    o->update_variant = B200LP_UPDATE_AUTO;
+    o->max_pivots = (int64_t)1 << 40;
+    o->eps_cost = 1e-9;
+    o->eps_pivot = 1e-9;
+    o->eps_feas = 1e-7;
+    o->check_every = 0;
+    o->use_graph = 1;
+}
+
+B200LP_API int b200lp_create(b200lp_solver** out, int device) {
+    if (!out) return fail(B200LP_E_INVALID, "out is NULL");
+    *out = nullptr;
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0)
+        return fail(B200LP_E_CUDA, "no CUDA device (%s); libb200lp has no CPU fallback",
+                    e != cudaSuccess ? cudaGetErrorString(e) : "device count 0");
+    if (device < 0 || device >= count) return fail(B200LP_E_INVALID, "device %d out of range [0,%d)", device, count);
+    b200lp_solver* s = new b200lp_solver();
+    s->device = device;
+    CK(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, device));
+    s->sm_count = prop.multiProcessorCount;
+    CK(cudaStreamCreateWithFlags(&s->own_stream, cudaStreamNonBlocking));
+    s->stream = s->own_stream;
+    CK(cudaEventCreate(&s->ev0));
+    CK(cudaEventCreate(&s->ev1));
+    CK(cudaEventCreateWithFlags(&s->ev_state[0], cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&s->ev_state[1], cudaEventDisableTiming));
+    CK(cudaMallocHost(&s->st_host, 2 * sizeof(DevState)));
+    CKR(s->st.ensure(1));
+    CK(cudaMemsetAsync(s->st.p, 0, sizeof(DevState), s->stream));
+    CKR(s->part_price.ensure(1024));
+    CKR(s->part_ratio.ensure(1024));
+    CKR(s->sfun.ensure(1));
+    CK(cudaFuncSetAttribute(k_update_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TMA_SMEM_BYTES));
+    CK(cudaStreamSynchronize(s->stream));
+    *out = s;
+    return 0;
+}
+
+B200LP_API int b200lp_destroy(b200lp_solver* s) {
+    if (!s) return 0;
+    cudaSetDevice(s->device);
+    cudaStreamSynchronize(s->stream);
+    if (s->graph) cudaGraphExecDestroy(s->graph);
+    s->own_T.release();
+    s->rowlab.release();
+    s->collab.release();
+    s->col.release();
+    s->part_price.release();
+    s->part_ratio.release();
+    s->st.release();
+    s->h_row.release();
+    s->h_col.release();
+    s->h_enter.release();
+    s->h_leave.release();
+    s->sA.release();
+    s->sb.release();
+    s->sc.release();
+    s->sx.release();
+    s->sfun.release();
+    s->sinfo.release();
+    s->sops.release();
+    s->sstatus.release();
+    s->snpiv.release();
+    s->slog.release();
+    if (s->st_host) cudaFreeHost(s->st_host);
+    cudaEventDestroy(s->ev0);
+    cudaEventDestroy(s->ev1);
+    cudaEventDestroy(s->ev_state[0]);
+    cudaEventDestroy(s->ev_state[1]);
+    if (s->own_stream) cudaStreamDestroy(s->own_stream);
+    delete s;
+    return 0;
+}
+
+B200LP_API int b200lp_set_stream(b200lp_solver* s, void* stream) {
+    if (!s) return fail(B200LP_E_INVALID, "solver is NULL");
+    s->stream = stream ? (cudaStream_t)stream : s->own_stream;
+    if (s->graph) {
+        cudaGraphExecDestroy(s->graph);
+        s->graph = nullptr;
+        s->graph_key = GraphKey();
+    }
+    return 0;
+}
+
+B200LP_API int b200lp_synchronize(b200lp_solver* s) {
+    if (!s) return fail(B200LP_E_INVALID, "solver is NULL");
+    CKR(set_device(s));
+    CK(cudaStreamSynchronize(s->stream));
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------------
+// tableau binding
+// ------------------------------------------------------------------------------------------------------
+static int ensure_aux(b200lp_solver* s, int64_t R, int64_t C) {
+    CKR(s->rowlab.ensure((size_t)R));
+    CKR(s->collab.ensure((size_t)C + 1));
+    CKR(s->col.ensure((size_t)R));
+    return 0;
+}
+
+static int ensure_hist(b200lp_solver* s, int64_t cap) {
+    cap = std::max<int64_t>(cap, 16);
+    if (cap > s->hist_cap) {
+        CKR(s->h_row.ensure((size_t)cap));
+        CKR(s->h_col.ensure((size_t)cap));
+        CKR(s->h_enter.ensure((size_t)cap));
+        CKR(s->h_leave.ensure((size_t)cap));
+        s->hist_cap = cap;
+    }
+    return 0;
+}
+
+static int bind(b200lp_solver* s, double* T, int64_t m, int64_t n_obj, int64_t C, int64_t ld, int64_t n_struct,
+                int32_t art_base) {
+    if (!T) return fail(B200LP_E_INVALID, "tableau pointer is NULL");
+    if (m < 0 || (n_obj != 1 && n_obj != 2) || C < 1) return fail(B200LP_E_INVALID, "bad tableau shape m=%lld n_obj=%lld C=%lld", (long long)m, (long long)n_obj, (long long)C);
+    if (ld < C || (ld & 1)) return fail(B200LP_E_INVALID, "row stride ld=%lld must be even and >= C=%lld", (long long)ld, (long long)C);
+    if (((uintptr_t)T) & 15) return fail(B200LP_E_INVALID, "tableau base must be 16-byte aligned");
+    if (m + n_obj > 0x7fffffff || C > 0x7fffffff) return fail(B200LP_E_INVALID, "tableau dimensions exceed int32 positions");
+    s->T = T;
+    s->m = m;
+    s->n_obj = n_obj;
+    s->R = m + n_obj;
+    s->C = C;
+    s->ld = ld;
+    s->n_struct = n_struct;
+    s->art_base = art_base;
+    CKR(ensure_aux(s, s->R, s->C));
+    return 0;
+}
+
+B200LP_API int b200lp_attach(b200lp_solver* s, double* T_dev, int64_t m, int64_t n_obj, int64_t C, int64_t ld,
+                             int64_t n_struct, int32_t art_base) {
+    if (!s) return fail(B200LP_E_INVALID, "solver is NULL");
+    CKR(set_device(s));
+    CKR(bind(s, T_dev, m, n_obj, C, ld, n_struct, art_base));
+    CK(cudaMemsetAsync(s->st.p, 0, sizeof(DevState), s->stream));
+    return 0;
+}
+
+B200LP_API int b200lp_dims(b200lp_solver* s, int64_t* m, int64_t* n_obj, int64_t* C, int64_t* ld) {
+    if (!s || !s->T) return fail(B200LP_E_STATE, "no tableau bound");
+    if (m) *m = s->m;
+    if (n_obj) *n_obj = s->n_obj;
+    if (C) *C = s->C;
+    if (ld) *ld = s->ld;
+    return 0;
+}
+
+B200LP_API int b200lp_generate(b200lp_solver* s, uint64_t seed, int64_t n_total, int64_t lab0) {
+    if (!s || !s->T) return fail(B200LP_E_STATE, "no tableau bound");
+    if (s->n_obj != 1) return fail(B200LP_E_INVALID, "generated tableaux have one objective row");
+    CKR(set_device(s));
+    s->n_struct = n_total;
+    s->art_base = (int32_t)(n_total + s->m);
+    dim3 grid((unsigned)((s->ld / 2 + 255) / 256), (unsigned)std::min<int64_t>(s->R, 2048));
+    k_generate<<<grid, 256, 0, s->stream>>>(s->T, s->m, s->R, s->C, s->ld, seed, n_total, lab0, s->rowlab.p, s->collab.p);
+    s->launches++;
+    CK(cudaGetLastError());
+    CK(cudaMemsetAsync(s->st.p, 0, sizeof(DevState), s->stream));
+    return 0;
+}
+
+B200LP_API int b200lp_set_labels(b200lp_solver* s, const int32_t* rowlab, const int32_t* collab) {
+    if (!s || !s->T) return fail(B200LP_E_STATE, "no tableau bound");
+    CKR(set_device(s));
+    if (rowlab) CK(cudaMemcpyAsync(s->rowlab.p, rowlab, (size_t)s->R * 4, cudaMemcpyHostToDevice, s->stream));
+    if (collab) CK(cudaMemcpyAsync(s->collab.p, collab, (size_t)s->C * 4, cudaMemcpyHostToDevice, s->stream));
+    CK(cudaStreamSynchronize(s->stream));
+    return 0;
+}
+
+B200LP_API int b200lp_get_labels(b200lp_solver* s, int32_t* rowlab, int32_t* collab) {
+    if (!s || !s->T) return fail(B200LP_E_STATE, "no tableau bound");
+    CKR(set_device(s));
+    if (rowlab) CK(cudaMemcpyAsync(rowlab, s->rowlab.p, (size_t)s->R * 4, cudaMemcpyDeviceToHost, s->stream));
+    if (collab) CK(cudaMemcpyAsync(collab, s->collab.p, (size_t)s->C * 4, cudaMemcpyDeviceToHost, s->stream));
+    CK(cudaStreamSynchronize(s->stream));
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------------
+// launches
+// ------------------------------------------------------------------------------------------------------
+static inline int clampi(int64_t v, int64_t lo, int64_t hi) { return (int)std::max(lo, std::min(hi, v)); }
+
+static int launch_flush(b200lp_solver* s) {
+    const int blocks = clampi((s->C + PICK_THREADS - 1) / PICK_THREADS, 1, 2 * s->sm_count);
+    k_flush_row<<<blocks, PICK_THREADS, 0, s->stream>>>(s->T, s->C, s->ld, s->st.p);
+    k_clear_pend<<<1, 1, 0, s->stream>>>(s->st.p);
+    s->launches += 2;
+    CK(cudaGetLastError());
+    return 0;
+}
+
+static int launch_price(b200lp_solver* s, int64_t obj_row, int32_t rule, double eps_cost, bool sharded) {
+    const int blocks = clampi((s->C + PICK_THREADS * 4 - 1) / (PICK_THREADS * 4), 1, 2 * s->sm_count);
+#define PRICE(BL, SH) \
+    k_price<BL, SH><<<blocks, PICK_THREADS, 0, s->stream>>>(s->T, s->C, s->ld, obj_row, s->collab.p, s->art_base, eps_cost, s->st.p, s->part_price.p)
+    if (rule == B200LP_RULE_BLAND) {
+        if (sharded) PRICE(true, true);
+        else PRICE(true, false);
+    } else {
+        if (sharded) PRICE(false, true);
+        else PRICE(false, false);
+    }
+#undef PRICE
+    s->launches++;
+    CK(cudaGetLastError());
+    return 0;
+}
+
+static int launch_ratio(b200lp_solver* s, double eps_pivot, bool row_preset, const double* ext, int64_t ext_stride) {
+    const int blocks = clampi((s->R + PICK_THREADS - 1) / PICK_THREADS, 1, 2 * s->sm_count);
+    if (row_preset)
+        k_ratio<true><<<blocks, PICK_THREADS, 0, s->stream>>>(s->T, s->R, s->m, s->C, s->ld, s->rowlab.p, s->collab.p, eps_pivot,
+                                                              s->st.p, s->part_ratio.p, s->col.p, ext, ext_stride, s->h_row.p,
+                                                              s->h_col.p, s->h_enter.p, s->h_leave.p, s->hist_cap);
+    else
+        k_ratio<false><<<blocks, PICK_THREADS, 0, s->stream>>>(s->T, s->R, s->m, s->C, s->ld, s->rowlab.p, s->collab.p, eps_pivot,
+                                                               s->st.p, s->part_ratio.p, s->col.p, ext, ext_stride, s->h_row.p,
+                                                               s->h_col.p, s->h_enter.p, s->h_leave.p, s->hist_cap);
+    s->launches++;
+    CK(cudaGetLastError());
+    return 0;
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static int ensure_tmap(b200lp_solver* s) {
+    if (s->tmap_T == s->T && s->tmap_R == s->R && s->tmap_C == s->C && s->tmap_ld == s->ld) return 0;
+    static EncodeTiledFn encode = nullptr;
+    if (!encode) {
+        void* fn = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        CK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q));
+        if (!fn || q != cudaDriverEntryPointSuccess) return fail(B200LP_E_CUDA, "cuTensorMapEncodeTiled not available");
+        encode = (EncodeTiledFn)fn;
+    }
+    cuuint64_t dims[2] = {(cuuint64_t)s->C, (cuuint64_t)s->R};
+    cuuint64_t strides[1] = {(cuuint64_t)s->ld * 8};
+    cuuint32_t box[2] = {(cuuint32_t)TMA_BOX_C, (cuuint32_t)TMA_BOX_R};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = encode(&s->tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, (void*)s->T, dims, strides, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(B200LP_E_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+    s->tmap_T = s->T;
+    s->tmap_R = s->R;
+    s->tmap_C = s->C;
+    s->tmap_ld = s->ld;
+    return 0;
+}
+
+static int resolve_variant(const b200lp_solver* s, int32_t v) {
+    if (v == B200LP_UPDATE_LDG || v == B200LP_UPDATE_TMA) return v;
+    (void)s;
+    return B200LP_UPDATE_LDG;
+}
+
+static int launch_update(b200lp_solver* s, int32_t variant) {
+    variant = resolve_variant(s, variant);
+    if (variant == B200LP_UPDATE_TMA) {
+        CKR(ensure_tmap(s));
+        const int64_t strips = (s->C + TMA_BOX_C - 1) / TMA_BOX_C;
+        const int64_t row_tiles = (s->R + TMA_BOX_R - 1) / TMA_BOX_R;
+        int64_t chunk = std::max<int64_t>(1, row_tiles * strips / ((int64_t)s->sm_count * 6));
+        const int64_t n_chunks = (row_tiles + chunk - 1) / chunk;
+        const int64_t n_work = strips * n_chunks;
+        const int grid = clampi(n_work, 1, s->sm_count);
+        k_update_tma<<<grid, TMA_THREADS, TMA_SMEM_BYTES, s->stream>>>(s->tmap, s->T, s->R, s->C, s->ld, s->col.p, s->st.p,
+                                                                     (int)strips, (int)chunk, n_work);
+    } else {
+        const bool wide = s->C >= 2048;
+        const int nt = wide ? 256 : 128;
+        const int tiles_c = (int)((s->C + 2 * nt - 1) / (2 * nt));
+        int64_t tr = s->R * tiles_c / ((int64_t)s->sm_count * 8);
+        tr = std::max<int64_t>(8, std::min<int64_t>(64, tr / 8 * 8));
+        const int64_t n_tiles = (s->R + tr - 1) / tr * tiles_c;
+        const int grid = clampi(n_tiles, 1, (int64_t)s->sm_count * 16);
+        if (wide)
+            k_update_ldg<256, 8><<<grid, 256, 0, s->stream>>>(s->T, s->R, s->C, s->ld, s->col.p, s->st.p, (int)tr, tiles_c, n_tiles);
+        else
+            k_update_ldg<128, 8><<<grid, 128, 0, s->stream>>>(s->T, s->R, s->C, s->ld, s->col.p, s->st.p, (int)tr, tiles_c, n_tiles);
+    }
+    s->launches++;
+    CK(cudaGetLastError());
+    return 0;
+}
+
+static int launch_reset(b200lp_solver* s, int64_t max_pivots, bool keep_count) {
+    k_reset_state<<<1, 1, 0, s->stream>>>(s->st.p, (long long)max_pivots, keep_count ? 1 : 0);
+    s->launches++;
+    CK(cudaGetLastError());
+    return 0;
+}
+
+// one iteration of the loop on the stream
+static int enqueue_iteration(b200lp_solver* s, const b200lp_opts* o, int64_t obj_row) {
+    CKR(launch_price(s, obj_row, o->rule, o->eps_cost, false));
+    CKR(launch_ratio(s, o->eps_pivot, false, nullptr, 0));
+    CKR(launch_update(s, o->update_variant));
+    return 0;
+}
+
+static int enqueue_driveout(b200lp_solver* s, const b200lp_opts* o) {
+    CKR(launch_flush(s));
+    k_driveout_pick<<<1, 1024, 0, s->stream>>>(s->T, s->m, s->C, s->ld, s->rowlab.p, s->collab.p, s->art_base, o->eps_pivot, s->st.p);
+    s->launches++;
+    CK(cudaGetLastError());
+    CKR(launch_ratio(s, o->eps_pivot, true, nullptr, 0));
+    CKR(launch_update(s, o->update_variant));
+    return 0;
+}
+
+static int default_check_every(const b200lp_solver* s) {
+    // enough work per replay to hide the host's status read; big tableaux need few pivots per replay
+    const double bytes = 16.0 * (double)s->R * (double)s->C;
+    if (bytes > 1e9) return 8;
+    if (bytes > 5e7) return 32;
+    return 64;
+}
+
+static int get_graph(b200lp_solver* s, const b200lp_opts* o, int64_t obj_row, int iters) {
+    GraphKey k;
+    k.T = s->T;
+    k.R = s->R;
+    k.C = s->C;
+    k.ld = s->ld;
+    k.obj_row = obj_row;
+    k.rule = o->rule;
+    k.variant = resolve_variant(s, o->update_variant);
+    k.iters = iters;
+    k.eps_cost = o->eps_cost;
+    k.eps_pivot = o->eps_pivot;
+    k.hist_cap = s->hist_cap;
+    if (s->graph && k == s->graph_key) return 0;
+    if (s->graph) {
+        cudaGraphExecDestroy(s->graph);
+        s->graph = nullptr;
+    }
+    if (k.variant == B200LP_UPDATE_TMA) CKR(ensure_tmap(s));
+    const int64_t before = s->launches;
+    cudaGraph_t g = nullptr;
+    CK(cudaStreamBeginCapture(s->stream, cudaStreamCaptureModeThreadLocal));
+    int rc = 0;
+    for (int i = 0; i < iters && !rc; ++i) rc = enqueue_iteration(s, o, obj_row);
+    cudaError_t e = cudaStreamEndCapture(s->stream, &g);
+    s->launches = before;  // capture launched nothing
+    if (rc) {
+        if (g) cudaGraphDestroy(g);
+        return rc;
+    }
+    if (e != cudaSuccess) return fail(B200LP_E_CUDA, "graph capture failed: %s", cudaGetErrorString(e));
+    e = cudaGraphInstantiate(&s->graph, g, 0);
+    cudaGraphDestroy(g);
+    if (e != cudaSuccess) return fail(B200LP_E_CUDA, "cudaGraphInstantiate failed: %s", cudaGetErrorString(e));
+    s->graph_key = k;
+    return 0;
+}
+
+// Runs chunks of iterations until the device reports done.  mode 0: pricing loop on obj_row; mode 1: drive-out.
+static int run_loop(b200lp_solver* s, const b200lp_opts* o, int64_t obj_row, int mode, DevState* final_state) {
+    int iters = o->check_every > 0 ? o->check_every : default_check_every(s);
+    if (mode == 1) iters = std::min(iters, 8);
+    const bool use_graph = o->use_graph && mode == 0;
+    if (use_graph) CKR(get_graph(s, o, obj_row, iters));
+    const int per_iter = 3;
+    int slot = 0;
+    bool first = true;
+    for (;;) {
+        if (use_graph) {
+            CK(cudaGraphLaunch(s->graph, s->stream));
+            s->launches += (int64_t)per_iter * iters;
+        } else {
+            for (int i = 0; i < iters; ++i) {
+                if (mode == 0) CKR(enqueue_iteration(s, o, obj_row));
+                else CKR(enqueue_driveout(s, o));
+            }
+        }
+        CK(cudaMemcpyAsync(&s->st_host[slot], s->st.p, sizeof(DevState), cudaMemcpyDeviceToHost, s->stream));
+        CK(cudaEventRecord(s->ev_state[slot], s->stream));
+        if (!first) {
+            // look at the PREVIOUS chunk's state while this chunk runs
+            CK(cudaEventSynchronize(s->ev_state[slot ^ 1]));
+            if (s->st_host[slot ^ 1].done) break;
+        }
+        first = false;
+        slot ^= 1;
+    }
+    CK(cudaStreamSynchronize(s->stream));
+    // the newest copy is at least as recent as the one that reported done
+    const DevState& a = s->st_host[slot];
+    *final_state = a.done ? a : s->st_host[slot ^ 1];
+    return 0;
+}
+
+static int copy_history(b200lp_solver* s, b200lp_result* r, int64_t n) {
+    if (!r || r->hist_cap <= 0) return 0;
+    const int64_t k = std::min<int64_t>(std::min<int64_t>(n, r->hist_cap), s->hist_cap);
+    if (k <= 0) return 0;
+    if (r->piv_row) CK(cudaMemcpyAsync(r->piv_row, s->h_row.p, (size_t)k * 4, cudaMemcpyDeviceToHost, s->stream));
+    if (r->piv_col) CK(cudaMemcpyAsync(r->piv_col, s->h_col.p, (size_t)k * 4, cudaMemcpyDeviceToHost, s->stream));
+    if (r->enter_lab) CK(cudaMemcpyAsync(r->enter_lab, s->h_enter.p, (size_t)k * 4, cudaMemcpyDeviceToHost, s->stream));
+    if (r->leave_lab) CK(cudaMemcpyAsync(r->leave_lab, s->h_leave.p, (size_t)k * 4, cudaMemcpyDeviceToHost, s->stream));
+    CK(cudaStreamSynchronize(s->stream));
+    return 0;
+}
+
+static int read_solution_impl(b200lp_solver* s, double* x_host, double* fun) {
+    CKR(launch_flush(s));
+    CKR(s->sx.ensure((size_t)std::max<int64_t>(1, s->n_struct)));
+    CK(cudaMemsetAsync(s->sx.p, 0, (size_t)std::max<int64_t>(1, s->n_struct) * 8, s->stream));
+    const int blocks = clampi((std::max<int64_t>(s->m, 1) + 255) / 256, 1, 1 << 30);
+    k_read_solution<<<blocks, 256, 0, s->stream>>>(s->T, s->m, s->C, s->ld, s->rowlab.p, s->n_struct, s->sx.p, s->sfun.p);
+    s->launches++;
+    CK(cudaGetLastError());
+    if (x_host && s->n_struct > 0) CK(cudaMemcpyAsync(x_host, s->sx.p, (size_t)s->n_struct * 8, cudaMemcpyDeviceToHost, s->stream));
+    if (fun) CK(cudaMemcpyAsync(fun, s->sfun.p, 8, cudaMemcpyDeviceToHost, s->stream));
+    CK(cudaStreamSynchronize(s->stream));
+    return 0;
+}
+
+B200LP_API int b200lp_read_solution(b200lp_solver* s, double* x_host, double* fun) {
+    if (!s || !s->T) return fail(B200LP_E_STATE, "no tableau bound");
+    CKR(set_device(s));
+    return read_solution_impl(s, x_host, fun);
+}
+
+B200LP_API int b200lp_read_tableau(b200lp_solver* s, double* T_host) {
+    if (!s || !s->T) return fail(B200LP_E_STATE, "no tableau bound");
+    if (!T_host) return fail(B200LP_E_INVALID, "T_host is NULL");
+    CKR(set_device(s));
+    CKR(launch_flush(s));
+    CK(cudaMemcpy2DAsync(T_host, (size_t)s->C * 8, s->T, (size_t)s->ld * 8, (size_t)s->C * 8, (size_t)s->R,
+                         cudaMemcpyDeviceToHost, s->stream));
+    CK(cudaStreamSynchronize(s->stream));
+    return 0;
+}
+
+static int check_opts(const b200lp_opts* o) {
+    if (!o) return fail(B200LP_E_INVALID, "opts is NULL");
+    if (o->rule != B200LP_RULE_DANTZIG && o->rule != B200LP_RULE_BLAND) return fail(B200LP_E_INVALID, "unknown rule %d", o->rule);
+    if (o->update_variant < 0 || o->update_variant > 2) return fail(B200LP_E_INVALID, "unknown update variant %d", o->update_variant);
+    if (o->max_pivots < 0) return fail(B200LP_E_INVALID, "max_pivots < 0");
+    return 0;
+}
+
+B200LP_API int b200lp_run(b200lp_solver* s, const b200lp_opts* o, int64_t obj_row, b200lp_result* r) {
+    if (!s || !s->T) return fail(B200LP_E_STATE, "no tableau bound");
+    CKR(check_opts(o));
+    if (obj_row < s->m || obj_row >= s->R) return fail(B200LP_E_INVALID, "obj_row %lld is not an objective row", (long long)obj_row);
+    CKR(set_device(s));
+    const int64_t l0 = s->launches;
+    CKR(ensure_hist(s, std::min<int64_t>(o->max_pivots, r && r->hist_cap > 0 ? r->hist_cap : 16)));
+    CKR(launch_reset(s, o->max_pivots, false));
+    DevState fin;
+    CK(cudaEventRecord(s->ev0, s->stream));
+    CKR(run_loop(s, o, obj_row, 0, &fin));
+    CKR(launch_flush(s));
+    CK(cudaEventRecord(s->ev1, s->stream));
+    CK(cudaStreamSynchronize(s->stream));
+    if (r) {
+        float ms = 0.f;
+        CK(cudaEventElapsedTime(&ms, s->ev0, s->ev1));
+        r->status = fin.status;
+        r->n_pivots = fin.n_pivots;
+        r->n_phase1 = 0;
+        r->device_ms = ms;
+        CKR(read_solution_impl(s, r->x_len >= s->n_struct ? r->x : nullptr, &r->fun));
+        CKR(copy_history(s, r, fin.n_pivots));
+        r->kernel_launches = s->launches - l0;
+    }
+    return 0;
+}
+
+B200LP_API int b200lp_solve(b200lp_solver* s, const b200lp_opts* o, b200lp_result* r) {
+    if (!s || !s->T) return fail(B200LP_E_STATE, "no tableau bound");
+    CKR(check_opts(o));
+    CKR(set_device(s));
+    const int64_t l0 = s->launches;
+    CKR(ensure_hist(s, std::min<int64_t>(o->max_pivots, r && r->hist_cap > 0 ? r->hist_cap : 16)));
+    CKR(launch_reset(s, o->max_pivots, false));
+    DevState fin;
+    memset(&fin, 0, sizeof(fin));
+    int status = B200LP_STATUS_OPTIMAL;
+    int64_t n_phase1 = 0;
+    CK(cudaEventRecord(s->ev0, s->stream));
+    if (s->n_obj == 2) {
+        CKR(run_loop(s, o, s->m + 1, 0, &fin));
+        status = fin.status;
+        if (status == B200LP_STATUS_UNBOUNDED) status = B200LP_STATUS_NUMERICAL;
+        if (status == B200LP_STATUS_OPTIMAL) {
+            CKR(launch_flush(s));
+            double w = 0.0;
+            CK(cudaMemcpyAsync(&w, s->T + (s->m + 1) * s->ld + s->C - 1, 8, cudaMemcpyDeviceToHost, s->stream));
+            CK(cudaStreamSynchronize(s->stream));
+            if (w < -o->eps_feas) status = B200LP_STATUS_INFEASIBLE;
+        }
+        if (status == B200LP_STATUS_OPTIMAL) {
+            CKR(launch_reset(s, o->max_pivots, true));
+            CKR(run_loop(s, o, s->m, 1, &fin));
+            status = fin.status;
+        }
+        n_phase1 = fin.n_pivots;
+    }
+    if (status == B200LP_STATUS_OPTIMAL) {
+        CKR(launch_reset(s, o->max_pivots, true));
+        CKR(run_loop(s, o, s->m, 0, &fin));
+        status = fin.status;
+    }
+    CKR(launch_flush(s));
+    CK(cudaEventRecord(s->ev1, s->stream));
+    CK(cudaStreamSynchronize(s->stream));
+    if (r) {
+        float ms = 0.f;
+        CK(cudaEventElapsedTime(&ms, s->ev0, s->ev1));
+        r->status = status;
+        r->n_pivots = fin.n_pivots;
+        r->n_phase1 = n_phase1;
+        r->device_ms = ms;
+        CKR(read_solution_impl(s, r->x_len >= s->n_struct ? r->x : nullptr, &r->fun));
+        CKR(copy_history(s, r, fin.n_pivots));
+        r->kernel_launches = s->launches - l0;
+    }
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------------
+// one LP from arrays (the linprog seam)
+// ------------------------------------------------------------------------------------------------------
+B200LP_API int b200lp_solve_dense(b200lp_solver* s, const b200lp_problem* p, const b200lp_opts* o, b200lp_result* r) {
+    if (!s) return fail(B200LP_E_INVALID, "solver is NULL");
+    if (!p || !r) return fail(B200LP_E_INVALID, "problem/result is NULL");
+    CKR(check_opts(o));
+    const int64_t m = p->m, n = p->n;
+    if (m < 0 || n < 0) return fail(B200LP_E_INVALID, "negative dimensions");
+    if (n > 0 && !p->c) return fail(B200LP_E_INVALID, "c is NULL");
+    if (m > 0 && (!p->b || !p->ops || (n > 0 && !p->A))) return fail(B200LP_E_INVALID, "A, b or ops is NULL");
+    const int64_t lda = p->lda > 0 ? p->lda : n;
+    if (lda < n) return fail(B200LP_E_INVALID, "lda < n");
+    CKR(set_device(s));
+    const int64_t l0 = s->launches;
+
+    // b decides the row normalisation; with device inputs it is the only array read back (m doubles)
+    std::vector<double> bh((size_t)m);
+    if (m > 0) {
+        if (p->on_device) {
+            CK(cudaMemcpyAsync(bh.data(), p->b, (size_t)m * 8, cudaMemcpyDeviceToHost, s->stream));
+            CK(cudaStreamSynchronize(s->stream));
+        } else {
+            memcpy(bh.data(), p->b, (size_t)m * 8);
+        }
+    }
+    std::vector<RowInfo> info((size_t)m);
+    std::vector<int32_t> rowlab((size_t)m + 2, -1);
+    int64_t n_ge = 0, n_art = 0;
+    const int32_t art_base = (int32_t)(n + m);
+    for (int64_t i = 0; i < m; ++i) {
+        int op = p->ops[i];
+        if (op < 0 || op > 2) return fail(B200LP_E_INVALID, "ops[%lld] = %d is not L/G/E", (long long)i, op);
+        const bool neg = bh[(size_t)i] < 0.0;
+        if (neg && op != B200LP_OP_EQ) op = (op == B200LP_OP_LE) ? B200LP_OP_GE : B200LP_OP_LE;
+        info[(size_t)i].flags = (neg ? 1 : 0) | (op << 1);
+        info[(size_t)i].surplus = -1;
+        if (op == B200LP_OP_GE) info[(size_t)i].surplus = (int32_t)(n + n_ge++);
+        if (op != B200LP_OP_LE) ++n_art;
+        rowlab[(size_t)i] = (op == B200LP_OP_LE) ? (int32_t)(n + i) : (int32_t)(art_base + i);
+    }
+    const int64_t n_obj = n_art > 0 ? 2 : 1;
+    const int64_t C = n + n_ge + 1;
+    const int64_t R = m + n_obj;
+    const int64_t ld = (C + 15) / 16 * 16;
+    std::vector<int32_t> collab((size_t)C, -1);
+    for (int64_t j = 0; j < n; ++j) collab[(size_t)j] = (int32_t)j;
+    for (int64_t i = 0; i < m; ++i)
+        if (info[(size_t)i].surplus >= 0) collab[(size_t)info[(size_t)i].surplus] = (int32_t)(n + i);
+
+    CKR(s->own_T.ensure((size_t)(R * ld)));
+    CKR(bind(s, s->own_T.p, m, n_obj, C, ld, n, art_base));
+    CKR(s->sinfo.ensure((size_t)std::max<int64_t>(m, 1)));
+    const double *dA = p->A, *db = p->b, *dc = p->c;
+    int64_t dlda = lda;
+    if (!p->on_device) {
+        CKR(s->sA.ensure((size_t)std::max<int64_t>(m * n, 1)));
+        CKR(s->sb.ensure((size_t)std::max<int64_t>(m, 1)));
+        CKR(s->sc.ensure((size_t)std::max<int64_t>(n, 1)));
+        if (m > 0 && n > 0)
+            CK(cudaMemcpy2DAsync(s->sA.p, (size_t)n * 8, p->A, (size_t)lda * 8, (size_t)n * 8, (size_t)m, cudaMemcpyHostToDevice, s->stream));
+        if (m > 0) CK(cudaMemcpyAsync(s->sb.p, p->b, (size_t)m * 8, cudaMemcpyHostToDevice, s->stream));
+        if (n > 0) CK(cudaMemcpyAsync(s->sc.p, p->c, (size_t)n * 8, cudaMemcpyHostToDevice, s->stream));
+        dA = s->sA.p;
+        db = s->sb.p;
+        dc = s->sc.p;
+        dlda = n;
+    }
+    if (m > 0) CK(cudaMemcpyAsync(s->sinfo.p, info.data(), (size_t)m * sizeof(RowInfo), cudaMemcpyHostToDevice, s->stream));
+    CK(cudaMemcpyAsync(s->rowlab.p, rowlab.data(), (size_t)R * 4, cudaMemcpyHostToDevice, s->stream));
+    CK(cudaMemcpyAsync(s->collab.p, collab.data(), (size_t)C * 4, cudaMemcpyHostToDevice, s->stream));
+    {
+        dim3 grid((unsigned)((ld + 255) / 256), (unsigned)std::min<int64_t>(m + 1, 4096));
+        k_build_rows<<<grid, 256, 0, s->stream>>>(s->T, m, n, C, ld, dA, dlda, db, dc, s->sinfo.p);
+        s->launches++;
+        CK(cudaGetLastError());
+        if (n_obj == 2) {
+            k_build_phase1_row<<<(unsigned)((ld + 255) / 256), 256, 0, s->stream>>>(s->T, m, C, ld, s->rowlab.p, art_base);
+            s->launches++;
+            CK(cudaGetLastError());
+        }
+    }
+    // the host vectors above must outlive the async copies
+    CK(cudaStreamSynchronize(s->stream));
+    const int64_t built = s->launches - l0;
+    CKR(b200lp_solve(s, o, r));
+    r->kernel_launches += built;
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------------
+// single-phase entry points
+// ------------------------------------------------------------------------------------------------------
+static int read_state(b200lp_solver* s, DevState* out) {
+    CK(cudaMemcpyAsync(&s->st_host[0], s->st.p, sizeof(DevState), cudaMemcpyDeviceToHost, s->stream));
+    CK(cudaStreamSynchronize(s->stream));
+    *out = s->st_host[0];
+    return 0;
+}
+
+B200LP_API int b200lp_select_entering(b200lp_solver* s, int64_t obj_row, int32_t rule, double eps_cost, int64_t* col_out) {
+    if (!s || !s->T) return fail(B200LP_E_STATE, "no tableau bound");
+    if (obj_row < s->m || obj_row >= s->R) return fail(B200LP_E_INVALID, "obj_row %lld is not an objective row", (long long)obj_row);
+    CKR(set_device(s));
+    CKR(launch_flush(s));
+    CKR(launch_reset(s, (int64_t)1 << 40, true));
+    CKR(launch_price(s, obj_row, rule, eps_cost, false));
+    DevState st;
+    CKR(read_state(s, &st));
+    if (col_out) *col_out = st.have_pivot ? st.s : -1;
+    return 0;
+}
+
+B200LP_API int b200lp_ratio_test(b200lp_solver* s, int64_t col, double eps_pivot, int64_t* row_out) {
+    if (!s || !s->T) return fail(B200LP_E_STATE, "no tableau bound");
+    if (col < 0 || col >= s->C - 1) return fail(B200LP_E_INVALID, "column %lld out of range", (long long)col);
+    CKR(set_device(s));
+    CKR(launch_flush(s));
+    // dry run: take the decision on a scratch copy of the labels so that nothing is swapped or logged
+    std::vector<int32_t> rl((size_t)s->R), cl((size_t)s->C);
+    CKR(b200lp_get_labels(s, rl.data(), cl.data()));
+    DevState before;
+    CKR(read_state(s, &before));
+    CKR(ensure_hist(s, 16));
+    k_set_pivot<<<1, 1, 0, s->stream>>>(s->st.p, -1, (int32_t)col, s->collab.p);
+    s->launches++;
+    CKR(launch_ratio(s, eps_pivot, false, nullptr, 0));
+    DevState st;
+    CKR(read_state(s, &st));
+    if (row_out) *row_out = (st.status == B200LP_STATUS_UNBOUNDED && st.done) ? -1 : st.r;
+    // undo the bookkeeping of k_ratio
+    CKR(b200lp_set_labels(s, rl.data(), cl.data()));
+    before.ticket_price = before.ticket_ratio = 0;
+    CK(cudaMemcpyAsync(s->st.p, &before, sizeof(DevState), cudaMemcpyHostToDevice, s->stream));
+    CK(cudaStreamSynchronize(s->stream));
+    return 0;
+}
+
+B200LP_API int b200lp_pivot(b200lp_solver* s, int64_t row, int64_t col, int32_t update_variant) {
+    if (!s || !s->T) return fail(B200LP_E_STATE, "no tableau bound");
+    if (row < 0 || row >= s->m) return fail(B200LP_E_INVALID, "row %lld out of range", (long long)row);
+    if (col < 0 || col >= s->C - 1) return fail(B200LP_E_INVALID, "column %lld out of range", (long long)col);
+    CKR(set_device(s));
+    CKR(launch_flush(s));
+    CKR(ensure_hist(s, 16));
+    k_set_pivot<<<1, 1, 0, s->stream>>>(s->st.p, (int32_t)row, (int32_t)col, s->collab.p);
+    s->launches++;
+    CKR(launch_ratio(s, 0.0, true, nullptr, 0));
+    CKR(launch_update(s, update_variant));
+    CKR(launch_flush(s));
+    CK(cudaStreamSynchronize(s->stream));
+    return 0;
+}
+
+B200LP_API int b200lp_time_update(b200lp_solver* s, int64_t row, int64_t col, int32_t update_variant, int32_t reps,
+                                  double* ms_per_launch) {
+    if (!s || !s->T) return fail(B200LP_E_STATE, "no tableau bound");
+    if (row < 0 || row >= s->m || col < 0 || col >= s->C - 1 || reps < 1) return fail(B200LP_E_INVALID, "bad arguments");
+    CKR(set_device(s));
+    CKR(launch_flush(s));
+    CKR(ensure_hist(s, 16));
+    k_set_pivot<<<1, 1, 0, s->stream>>>(s->st.p, (int32_t)row, (int32_t)col, s->collab.p);
+    s->launches++;
+    CKR(launch_ratio(s, 0.0, true, nullptr, 0));
+    CKR(launch_update(s, update_variant));  // warm-up
+    CK(cudaEventRecord(s->ev0, s->stream));
+    for (int i = 0; i < reps; ++i) CKR(launch_update(s, update_variant));
+    CK(cudaEventRecord(s->ev1, s->stream));
+    CK(cudaStreamSynchronize(s->stream));
+    float ms = 0.f;
+    CK(cudaEventElapsedTime(&ms, s->ev0, s->ev1));
+    if (ms_per_launch) *ms_per_launch = (double)ms / reps;
+    CKR(launch_flush(s));
+    CK(cudaStreamSynchronize(s->stream));
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------------
+// column-sharded tableau
+// ------------------------------------------------------------------------------------------------------
+B200LP_API int b200lp_shard_reset(b200lp_solver* s, int64_t max_pivots) {
+    if (!s || !s->T) return fail(B200LP_E_STATE, "no tableau bound");
+    CKR(set_device(s));
+    CKR(launch_flush(s));
+    CKR(ensure_hist(s, std::min<int64_t>(max_pivots, (int64_t)1 << 20)));
+    CKR(launch_reset(s, max_pivots, false));
+    return 0;
+}
+
+B200LP_API int b200lp_shard_candidate(b200lp_solver* s, const b200lp_opts* o, int64_t obj_row, double* cand_dev) {
+    if (!s || !s->T) return fail(B200LP_E_STATE, "no tableau bound");
+    if (!cand_dev) return fail(B200LP_E_INVALID, "cand_dev is NULL");
+    CKR(check_opts(o));
+    CKR(set_device(s));
+    CKR(launch_price(s, obj_row, o->rule, o->eps_cost, true));
+    const int blocks = clampi((s->R + PICK_THREADS - 1) / PICK_THREADS, 1, 2 * s->sm_count);
+    k_shard_extract<<<blocks, PICK_THREADS, 0, s->stream>>>(s->T, s->R, s->ld, s->st.p, cand_dev);
+    s->launches++;
+    CK(cudaGetLastError());
+    return 0;
+}
+
+B200LP_API int b200lp_shard_pivot(b200lp_solver* s, const b200lp_opts* o, const double* gathered_dev, int32_t world,
+                                  int32_t rank) {
+    if (!s || !s->T) return fail(B200LP_E_STATE, "no tableau bound");
+    if (!gathered_dev || world < 1 || rank < 0 || rank >= world) return fail(B200LP_E_INVALID, "bad shard arguments");
+    CKR(check_opts(o));
+    CKR(set_device(s));
+    const int64_t stride = s->R + 2;
+    k_shard_winner<<<1, 32, 0, s->stream>>>(gathered_dev, stride, world, rank, o->rule == B200LP_RULE_BLAND, s->st.p);
+    s->launches++;
+    CK(cudaGetLastError());
+    CKR(launch_ratio(s, o->eps_pivot, false, gathered_dev, stride));
+    CKR(launch_update(s, o->update_variant));
+    return 0;
+}
+
+B200LP_API int b200lp_shard_state(b200lp_solver* s, int32_t* done, int32_t* status, int64_t* n_pivots) {
+    if (!s || !s->T) return fail(B200LP_E_STATE, "no tableau bound");
+    CKR(set_device(s));
+    DevState st;
+    CKR(read_state(s, &st));
+    if (done) *done = st.done;
+    if (status) *status = st.status;
+    if (n_pivots) *n_pivots = st.n_pivots;
+    return 0;
+}
+
+B200LP_API int b200lp_read_history(b200lp_solver* s, int64_t cap, int32_t* piv_row, int32_t* piv_col, int32_t* enter_lab,
+                                   int32_t* leave_lab, int64_t* n_out) {
+    if (!s || !s->T) return fail(B200LP_E_STATE, "no tableau bound");
+    CKR(set_device(s));
+    DevState st;
+    CKR(read_state(s, &st));
+    b200lp_result r;
+    memset(&r, 0, sizeof(r));
+    r.piv_row = piv_row;
+    r.piv_col = piv_col;
+    r.enter_lab = enter_lab;
+    r.leave_lab = leave_lab;
+    r.hist_cap = cap;
+    CKR(copy_history(s, &r, st.n_pivots));
+    if (n_out) *n_out = std::min<int64_t>(std::min<int64_t>(st.n_pivots, cap), s->hist_cap);
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------------
+// batched small LPs
+// ------------------------------------------------------------------------------------------------------
+B200LP_API int b200lp_solve_batched(b200lp_solver* s, int64_t B, int64_t m, int64_t n, const double* A, const double* b,
+                                    const double* c, const int8_t* ops, const b200lp_opts* o, int32_t* status, double* fun,
+                                    double* x, int32_t* n_pivots, int32_t* piv_log, int64_t log_cap, int32_t on_device,
+                                    double* device_ms) {
+    if (!s) return fail(B200LP_E_INVALID, "solver is NULL");
+    CKR(check_opts(o));
+    if (B < 0 || m < 0 || n < 1) return fail(B200LP_E_INVALID, "bad batch shape B=%lld m=%lld n=%lld", (long long)B, (long long)m, (long long)n);
+    if (B == 0) return 0;
+    if (!A && m > 0) return fail(B200LP_E_INVALID, "A is NULL");
+    if (!c || (m > 0 && (!b || !ops)) || !status || !fun || !n_pivots) return fail(B200LP_E_INVALID, "NULL argument");
+    CKR(set_device(s));
+
+    BatchedParams P;
+    memset(&P, 0, sizeof(P));
+    int64_t ld = n + m + 1;
+    if ((ld & 1) == 0) ++ld;
+    const int64_t R = m + 2;
+    size_t warp_bytes = (size_t)(R * ld + R) * 8 + (size_t)(R + ld) * 4;
+    warp_bytes = (warp_bytes + 15) / 16 * 16;
+    const size_t smem_max = 200 * 1024;
+    if (warp_bytes > smem_max)
+        return fail(B200LP_E_INVALID, "LP of %lld x %lld needs %zu bytes of shared memory per warp; use b200lp_solve_dense",
+                    (long long)m, (long long)n, warp_bytes);
+    int wpc = (int)std::min<size_t>(8, smem_max / warp_bytes);
+    // keep several CTAs per SM resident for latency hiding
+    while (wpc > 1 && (size_t)wpc * warp_bytes > 48 * 1024) --wpc;
+    const size_t smem = (size_t)wpc * warp_bytes;
+    CK(cudaFuncSetAttribute(k_solve_batched, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max));
+
+    const double *dA = A, *db = b, *dc = c;
+    const int8_t* dops = ops;
+    int32_t *dstatus = status, *dnp = n_pivots, *dlog = piv_log;
+    double *dfun = fun, *dx = x;
+    if (!on_device) {
+        CKR(s->sA.ensure((size_t)std::max<int64_t>(B * m * n, 1)));
+        CKR(s->sb.ensure((size_t)std::max<int64_t>(B * m, 1)));
+        CKR(s->sc.ensure((size_t)(B * n)));
+        CKR(s->sops.ensure((size_t)std::max<int64_t>(B * m, 1)));
+        CKR(s->sstatus.ensure((size_t)B));
+        CKR(s->snpiv.ensure((size_t)B));
+        CKR(s->sfun.ensure((size_t)B));
+        if (x) CKR(s->sx.ensure((size_t)(B * n)));
+        if (piv_log && log_cap > 0) CKR(s->slog.ensure((size_t)(B * log_cap * 2)));
+        if (m > 0) {
+            CK(cudaMemcpyAsync(s->sA.p, A, (size_t)(B * m * n) * 8, cudaMemcpyHostToDevice, s->stream));
+            CK(cudaMemcpyAsync(s->sb.p, b, (size_t)(B * m) * 8, cudaMemcpyHostToDevice, s->stream));
+            CK(cudaMemcpyAsync(s->sops.p, ops, (size_t)(B * m), cudaMemcpyHostToDevice, s->stream));
+        }
+        CK(cudaMemcpyAsync(s->sc.p, c, (size_t)(B * n) * 8, cudaMemcpyHostToDevice, s->stream));
+        dA = s->sA.p;
+        db = s->sb.p;
+        dc = s->sc.p;
+        dops = s->sops.p;
+        dstatus = s->sstatus.p;
+        dnp = s->snpiv.p;
+        dfun = s->sfun.p;
+        dx = x ? s->sx.p : nullptr;
+        dlog = (piv_log && log_cap > 0) ? s->slog.p : nullptr;
+    }
+    P.B = B;
+    P.m = (int32_t)m;
+    P.n = (int32_t)n;
+    P.ld = (int32_t)ld;
+    P.rule = o->rule;
+    P.max_pivots = (int32_t)std::min<int64_t>(o->max_pivots, 0x7fffffff);
+    P.log_cap = (int32_t)(dlog ? log_cap : 0);
+    P.eps_cost = o->eps_cost;
+    P.eps_pivot = o->eps_pivot;
+    P.eps_feas = o->eps_feas;
+    P.A = dA;
+    P.b = db;
+    P.c = dc;
+    P.ops = dops;
+    P.status = dstatus;
+    P.fun = dfun;
+    P.x = dx;
+    P.n_pivots = dnp;
+    P.piv_log = dlog;
+    P.warp_bytes = warp_bytes;
+    const int64_t blocks = (B + wpc - 1) / wpc;
+    CK(cudaEventRecord(s->ev0, s->stream));
+    k_solve_batched<<<(unsigned)blocks, wpc * 32, smem, s->stream>>>(P);
+    s->launches++;
+    CK(cudaGetLastError());
+    CK(cudaEventRecord(s->ev1, s->stream));
+    if (!on_device) {
+        CK(cudaMemcpyAsync(status, dstatus, (size_t)B * 4, cudaMemcpyDeviceToHost, s->stream));
+        CK(cudaMemcpyAsync(n_pivots, dnp, (size_t)B * 4, cudaMemcpyDeviceToHost, s->stream));
+        CK(cudaMemcpyAsync(fun, dfun, (size_t)B * 8, cudaMemcpyDeviceToHost, s->stream));
+        if (x) CK(cudaMemcpyAsync(x, dx, (size_t)(B * n) * 8, cudaMemcpyDeviceToHost, s->stream));
+        if (dlog) CK(cudaMemcpyAsync(piv_log, dlog, (size_t)(B * log_cap * 2) * 4, cudaMemcpyDeviceToHost, s->stream));
+    }
+    CK(cudaStreamSynchronize(s->stream));
+    if (device_ms) {
+        float ms = 0.f;
+        CK(cudaEventElapsedTime(&ms, s->ev0, s->ev1));
+        *device_ms = ms;
+    }
+    return 0;
+}

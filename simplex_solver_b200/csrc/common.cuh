@@ -1,0 +1,93 @@
+// common.cuh -- device state, reduction keys and small helpers shared by the kernels of libb200lp.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace b200lp {
+
+// Loop state, resident in device memory for the whole pivot loop: the host only reads it back every
+// `check_every` pivots (no host round trip per pivot).
+struct DevState {
+    int32_t done;        // loop finished: optimal for this phase, unbounded, or pivot limit
+    int32_t status;      // B200LP_STATUS_* (valid when done)
+    int32_t have_pivot;  // the current iteration has an entering column (set by price, cleared by ratio)
+    int32_t pend;        // row `r` of the last pivot still holds unscaled values (scaled by the next price)
+    int32_t s;           // entering column position in this tableau, -1 when it lives in another shard
+    int32_t r;           // leaving row
+    int32_t enter_lab;   // id of the entering variable
+    int32_t leave_lab;   // id of the leaving variable
+    int32_t win_rank;    // sharded runs: shard that owns the entering column
+    int32_t pad0;
+    double p;            // pivot element T[r][s]
+    double inv_p;        // 1 / p
+    double best_val;     // reduced cost of the entering column (diagnostic)
+    long long n_pivots;  // pivots done by this loop
+    long long max_pivots;
+    unsigned int ticket_price;  // last-block-done counters
+    unsigned int ticket_ratio;
+};
+
+// Candidate of a min-reduction with a total order => the result does not depend on reduction order.
+struct Key {
+    double v;     // reduced cost (price) or ratio (ratio test)
+    int32_t lab;  // variable id used for tie-breaking; INT32_MAX = no candidate
+    int32_t pos;  // position (column or row) in the stored tableau
+};
+
+#define B200LP_NO_LAB 0x7fffffff
+
+__device__ __forceinline__ Key key_none() {
+    Key k;
+    k.v = 0.0;
+    k.lab = B200LP_NO_LAB;
+    k.pos = -1;
+    return k;
+}
+
+// lexicographic (v, lab): used by Dantzig pricing and by the ratio test
+__device__ __forceinline__ bool key_less_val(const Key& a, const Key& b) {
+    if (a.lab == B200LP_NO_LAB) return false;
+    if (b.lab == B200LP_NO_LAB) return true;
+    return a.v < b.v || (a.v == b.v && a.lab < b.lab);
+}
+// Bland: lowest variable id
+__device__ __forceinline__ bool key_less_lab(const Key& a, const Key& b) { return a.lab < b.lab; }
+
+template <bool BY_LABEL>
+__device__ __forceinline__ Key key_min(const Key& a, const Key& b) {
+    if (BY_LABEL) return key_less_lab(b, a) ? b : a;
+    return key_less_val(b, a) ? b : a;
+}
+
+template <bool BY_LABEL>
+__device__ __forceinline__ Key warp_key_min(Key k) {
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+        Key o;
+        o.v = __shfl_xor_sync(0xffffffffu, k.v, off);
+        o.lab = __shfl_xor_sync(0xffffffffu, k.lab, off);
+        o.pos = __shfl_xor_sync(0xffffffffu, k.pos, off);
+        k = key_min<BY_LABEL>(k, o);
+    }
+    return k;
+}
+
+// CTA-wide min of a Key; result valid in every thread of warp 0.  smem: one Key per warp.
+template <bool BY_LABEL>
+__device__ __forceinline__ Key block_key_min(Key k, Key* smem) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = (blockDim.x + 31) >> 5;
+    k = warp_key_min<BY_LABEL>(k);
+    if (lane == 0) smem[warp] = k;
+    __syncthreads();
+    if (warp == 0) {
+        k = lane < nwarp ? smem[lane] : key_none();
+        k = warp_key_min<BY_LABEL>(k);
+    }
+    return k;
+}
+
+// streaming (evict-first) 128-bit accesses for tableau elements that are touched once per pivot
+__device__ __forceinline__ double2 ld_stream(const double2* p) { return __ldcs(p); }
+__device__ __forceinline__ void st_stream(double2* p, double2 v) { __stcs(p, v); }
+
+}  // namespace b200lp

@@ -1,0 +1,290 @@
+// kernels_batched.cuh -- B independent small LPs, one warp per LP, the whole two-phase solve in one launch.
+//
+// The condensed tableau ((m+2) x (n + #>= rows + 1) doubles; 9 KB for the 20 x 30 LPs of BASELINE config 3)
+// lives in shared memory for the life of the LP, so HBM sees only the inputs (A, b, c, ops) and the outputs.
+// Each lane owns whole columns (j = lane, lane+32, ...): the rank-1 update needs no intra-warp exchange beyond
+// a broadcast read of the saved pivot column, and consecutive lanes touch consecutive doubles (conflict-free).
+// The row stride is odd so that the strided column reads of the ratio test are conflict-free too.
+// Control flow is warp-uniform; every decision is a warp-shuffle reduction with a total order, so the pivot
+// sequence is bit-identical to oracle/simplex_oracle.c.
+//
+// Reference seam: one SolverController.run() per problem
+// (/root/reference/app/controllers/ui_controller.py:194-195, solver_controller.py:53-120).
+#pragma once
+#include "common.cuh"
+
+namespace b200lp {
+
+struct BatchedParams {
+    int64_t B;
+    int32_t m, n;
+    int32_t ld;         // odd row stride of the shared-memory tableau, >= n + m + 1
+    int32_t rule;
+    int32_t max_pivots;
+    int32_t log_cap;
+    double eps_cost, eps_pivot, eps_feas;
+    const double* A;
+    const double* b;
+    const double* c;
+    const int8_t* ops;
+    int32_t* status;
+    double* fun;
+    double* x;
+    int32_t* n_pivots;
+    int32_t* piv_log;
+    size_t warp_bytes;  // shared memory per warp
+};
+
+struct WarpLP {
+    double* T;
+    double* colbuf;
+    int32_t* rowlab;
+    int32_t* collab;
+    int32_t m, n, R, C, ld, art_base;
+};
+
+__device__ __forceinline__ void wlp_pivot(const WarpLP& w, int r, int s, int lane) {
+    for (int i = lane; i < w.R; i += 32) w.colbuf[i] = w.T[i * w.ld + s];
+    __syncwarp();
+    const double p = w.colbuf[r];
+    const double inv_p = 1.0 / p;
+    for (int j = lane; j < w.C; j += 32) {
+        const bool is_s = (j == s);
+        const double q = is_s ? inv_p : w.T[r * w.ld + j] / p;
+        for (int i = 0; i < w.R; ++i) {
+            if (i == r) continue;
+            double* cell = w.T + i * w.ld + j;
+            const double t = is_s ? 0.0 : *cell;
+            *cell = __fma_rn(-w.colbuf[i], q, t);
+        }
+        w.T[r * w.ld + j] = q;
+    }
+    __syncwarp();
+    if (lane == 0) {
+        const int32_t leave = w.rowlab[r];
+        w.rowlab[r] = w.collab[s];
+        w.collab[s] = leave;
+    }
+    __syncwarp();
+}
+
+template <bool BLAND>
+__device__ __forceinline__ int wlp_price(const WarpLP& w, int obj_row, double eps_cost, int lane) {
+    Key k = key_none();
+    const double* d = w.T + obj_row * w.ld;
+    for (int j = lane; j < w.C - 1; j += 32) {
+        const int32_t lab = w.collab[j];
+        const double v = d[j];
+        if (lab < w.art_base && v < -eps_cost) {
+            Key c;
+            c.v = v;
+            c.lab = lab;
+            c.pos = j;
+            k = key_min<BLAND>(k, c);
+        }
+    }
+    k = warp_key_min<BLAND>(k);
+    return k.pos;
+}
+
+__device__ __forceinline__ int wlp_ratio(const WarpLP& w, int s, double eps_pivot, int lane) {
+    Key k = key_none();
+    for (int i = lane; i < w.m; i += 32) {
+        const int32_t lab = w.rowlab[i];
+        const double a = w.T[i * w.ld + s];
+        if (lab >= 0 && a > eps_pivot) {
+            Key c;
+            c.v = w.T[i * w.ld + w.C - 1] / a;
+            c.lab = lab;
+            c.pos = i;
+            k = key_min<false>(k, c);
+        }
+    }
+    k = warp_key_min<false>(k);
+    return k.pos;
+}
+
+struct WarpRun {
+    int32_t n_pivots;
+    int32_t max_pivots;
+    int32_t log_cap;
+    int32_t* log;  // this LP's [log_cap][2] slice or nullptr
+};
+
+__device__ __forceinline__ void wlp_log(WarpRun& run, int r, int s, int lane) {
+    if (lane == 0 && run.log && run.n_pivots < run.log_cap) {
+        run.log[2 * run.n_pivots + 0] = r;
+        run.log[2 * run.n_pivots + 1] = s;
+    }
+    run.n_pivots++;
+}
+
+// one phase on objective row obj_row; returns a B200LP_STATUS_* code (0 = optimal for this row)
+__device__ __forceinline__ int wlp_run_phase(const WarpLP& w, int obj_row, int rule, double eps_cost, double eps_pivot,
+                                             WarpRun& run, int lane) {
+    for (;;) {
+        if (run.n_pivots >= run.max_pivots) return 1;
+        const int s = rule == 1 ? wlp_price<true>(w, obj_row, eps_cost, lane) : wlp_price<false>(w, obj_row, eps_cost, lane);
+        if (s < 0) return 0;
+        const int r = wlp_ratio(w, s, eps_pivot, lane);
+        if (r < 0) return 3;
+        wlp_log(run, r, s, lane);
+        wlp_pivot(w, r, s, lane);
+    }
+}
+
+__device__ __forceinline__ int wlp_drive_out(const WarpLP& w, double eps_pivot, WarpRun& run, int lane) {
+    for (int i = 0; i < w.m; ++i) {
+        if (w.rowlab[i] < w.art_base) continue;
+        Key k = key_none();
+        const double* row = w.T + i * w.ld;
+        for (int j = lane; j < w.C - 1; j += 32) {
+            const int32_t lab = w.collab[j];
+            const double a = fabs(row[j]);
+            if (lab < w.art_base && a > eps_pivot) {
+                Key c;
+                c.v = -a;
+                c.lab = lab;
+                c.pos = j;
+                k = key_min<false>(k, c);
+            }
+        }
+        k = warp_key_min<false>(k);
+        if (k.pos < 0) {
+            __syncwarp();
+            if (lane == 0) w.rowlab[i] = -1 - w.rowlab[i];
+            __syncwarp();
+            continue;
+        }
+        if (run.n_pivots >= run.max_pivots) return 1;
+        wlp_log(run, i, k.pos, lane);
+        wlp_pivot(w, i, k.pos, lane);
+    }
+    return 0;
+}
+
+__global__ void __launch_bounds__(256) k_solve_batched(const BatchedParams P) {
+    extern __shared__ __align__(16) uint8_t smem_batched[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpc = blockDim.x >> 5;
+    const int64_t lp = (int64_t)blockIdx.x * wpc + warp;
+    if (lp >= P.B) return;
+    const int m = P.m, n = P.n, ld = P.ld, R = m + 2;
+
+    WarpLP w;
+    uint8_t* base = smem_batched + (size_t)warp * P.warp_bytes;
+    w.T = reinterpret_cast<double*>(base);
+    w.colbuf = w.T + (size_t)R * ld;
+    w.rowlab = reinterpret_cast<int32_t*>(w.colbuf + R);
+    w.collab = w.rowlab + R;
+    w.m = m;
+    w.n = n;
+    w.ld = ld;
+    w.art_base = n + m;
+
+    const double* A = P.A + lp * m * n;
+    const double* b = P.b + lp * m;
+    const double* c = P.c + lp * n;
+    const int8_t* ops = P.ops + lp * m;
+
+    // ---- normalise rows (b < 0 -> negate), place surplus columns, label the slack / artificial basis ----
+    for (int e = lane; e < R * ld; e += 32) w.T[e] = 0.0;
+    for (int j = lane; j < ld; j += 32) w.collab[j] = j < n ? j : -1;
+    __syncwarp();
+    int n_ge = 0, n_art = 0;
+    for (int i0 = 0; i0 < m; i0 += 32) {
+        const int i = i0 + lane;
+        int op = 0;
+        bool neg = false;
+        if (i < m) {
+            op = ops[i];
+            neg = b[i] < 0.0;
+            if (neg && op != 2) op = (op == 0) ? 1 : 0;
+        }
+        const unsigned ge_mask = __ballot_sync(0xffffffffu, i < m && op == 1);
+        const unsigned art_mask = __ballot_sync(0xffffffffu, i < m && op != 0);
+        if (i < m) {
+            const double bi = b[i];
+            w.T[i * ld + (ld - 1)] = neg ? -bi : bi;  // parked in the last slot; moved to column C-1 below
+            if (op == 1) {
+                const int k = n_ge + __popc(ge_mask & ((1u << lane) - 1u));
+                w.T[i * ld + n + k] = -1.0;
+                w.collab[n + k] = n + i;
+            }
+            w.rowlab[i] = (op == 0) ? n + i : w.art_base + i;
+            // remember the sign flip in colbuf for the coefficient load below
+            w.colbuf[i] = neg ? -1.0 : 1.0;
+        }
+        n_ge += __popc(ge_mask);
+        n_art += __popc(art_mask);
+    }
+    __syncwarp();
+    const int C = n + n_ge + 1;
+    const int n_obj = n_art > 0 ? 2 : 1;
+    w.C = C;
+    w.R = m + n_obj;
+    if (C - 1 != ld - 1) {
+        for (int i = lane; i < m; i += 32) {
+            const double v = w.T[i * ld + (ld - 1)];
+            w.T[i * ld + (ld - 1)] = 0.0;
+            w.T[i * ld + (C - 1)] = v;
+        }
+    }
+    if (lane == 0) {
+        w.collab[C - 1] = -1;
+        w.rowlab[m] = -1;
+        w.rowlab[m + 1] = -1;
+    }
+    __syncwarp();
+    for (int e = lane; e < m * n; e += 32) {
+        const int i = e / n, j = e - i * n;
+        const double a = A[e];
+        w.T[i * ld + j] = (w.colbuf[i] < 0.0) ? -a : a;
+    }
+    for (int j = lane; j < n; j += 32) w.T[m * ld + j] = c[j];
+    __syncwarp();
+    if (n_obj == 2) {
+        for (int j = lane; j < C; j += 32) {
+            double acc = 0.0;
+            for (int i = 0; i < m; ++i)
+                if (w.rowlab[i] >= w.art_base) acc = __dadd_rn(acc, w.T[i * ld + j]);
+            w.T[(m + 1) * ld + j] = -acc;
+        }
+    }
+    __syncwarp();
+
+    // ---- two-phase solve ----
+    WarpRun run;
+    run.n_pivots = 0;
+    run.max_pivots = P.max_pivots;
+    run.log_cap = P.log_cap;
+    run.log = P.piv_log ? P.piv_log + lp * (int64_t)P.log_cap * 2 : nullptr;
+    if (run.log)
+        for (int e = lane; e < 2 * P.log_cap; e += 32) run.log[e] = -1;
+    __syncwarp();
+    int st = 0;
+    if (n_obj == 2) {
+        st = wlp_run_phase(w, m + 1, P.rule, P.eps_cost, P.eps_pivot, run, lane);
+        if (st == 3) st = 4;
+        if (st == 0 && w.T[(m + 1) * ld + C - 1] < -P.eps_feas) st = 2;
+        if (st == 0) st = wlp_drive_out(w, P.eps_pivot, run, lane);
+    }
+    if (st == 0) st = wlp_run_phase(w, m, P.rule, P.eps_cost, P.eps_pivot, run, lane);
+
+    // ---- results ----
+    if (P.x) {
+        double* x = P.x + lp * n;
+        for (int j = lane; j < n; j += 32) x[j] = 0.0;
+        __syncwarp();
+        for (int i = lane; i < m; i += 32) {
+            const int32_t lab = w.rowlab[i];
+            if (lab >= 0 && lab < n) x[lab] = w.T[i * ld + C - 1];
+        }
+    }
+    if (lane == 0) {
+        P.status[lp] = st;
+        P.fun[lp] = -w.T[m * ld + C - 1];
+        P.n_pivots[lp] = run.n_pivots;
+    }
+}
+
+}  // namespace b200lp

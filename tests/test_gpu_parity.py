@@ -1,0 +1,323 @@
+"""GPU parity: the CUDA path, called through the C ABI (libb200lp.so), against
+  (i)  the CPU oracle (oracle/simplex_oracle.c) bit for bit: pivot sequence, tableau entries, z, x;
+  (ii) the golden vectors produced by the reference's own solve path (tests/golden/reference_golden.json),
+       status identical and z* within 1e-9 relative (the tolerance BASELINE.json's north_star states).
+"""
+import numpy as np
+import pytest
+
+from simplex_solver_b200 import native, workloads as W
+from tests.helpers import assert_bit_equal, to_min_form, z_from_fun
+
+pytestmark = pytest.mark.gpu
+
+REL = 1e-9  # north_star: z* and x* within 1e-9 relative in fp64
+
+
+def _torch():
+    import torch
+    return torch
+
+
+def _device_tableau(solver, m, n_obj, C, n_struct, art_base):
+    torch = _torch()
+    ld = (C + 15) // 16 * 16
+    T = torch.empty((m + n_obj) * ld, dtype=torch.float64, device="cuda:0")
+    solver.attach(T.data_ptr(), m, n_obj, C, ld, n_struct, art_base, keep=T)
+    return T, ld
+
+
+# ---------------------------------------------------------------------------------------------------
+# reference known-answer problems through the linprog seam
+# ---------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("rule", [native.RULE_DANTZIG, native.RULE_BLAND])
+def test_kat_against_reference_golden_and_oracle(solver, oracle, golden, rule):
+    for name, g in golden["kat"].items():
+        A, b, c, ops, mx, _ = W.problem_dict_to_arrays(g["problem"])
+        cmin = to_min_form(c, mx)
+        got = solver.solve_dense(A, b, cmin, ops, native.make_opts(rule=rule), hist_cap=64)
+        ref = oracle.solve_lp(A, b, cmin, ops, oracle.make_opts(rule=rule), hist_cap=64)
+        assert got["status"] == g["scipy_status"], name
+        assert got["status"] == ref["status"], name
+        assert got["n_pivots"] == ref["n_pivots"] and got["n_phase1"] == ref["n_phase1"], name
+        np.testing.assert_array_equal(got["piv_row"], ref["piv_row"], err_msg=name)
+        np.testing.assert_array_equal(got["piv_col"], ref["piv_col"], err_msg=name)
+        np.testing.assert_array_equal(got["enter_lab"], ref["enter_lab"], err_msg=name)
+        np.testing.assert_array_equal(got["leave_lab"], ref["leave_lab"], err_msg=name)
+        if got["status"] == 0:
+            assert_bit_equal(got["fun"], ref["fun"], name + " fun")
+            assert_bit_equal(got["x"], ref["x"], name + " x")
+            z = z_from_fun(got["fun"], mx)
+            assert abs(z - g["z"]) <= REL * max(1.0, abs(g["z"])), name
+            if g["x_unique"]:
+                np.testing.assert_allclose(got["x"], g["x"], rtol=REL, atol=REL, err_msg=name)
+
+
+def test_mixed_operator_lps_against_reference_golden(solver, oracle, golden):
+    for k, g in enumerate(golden["mixed"]):
+        A = np.array(g["A"], dtype=np.float64).reshape(len(g["b"]), len(g["c"]))
+        b, c, ops = np.array(g["b"]), np.array(g["c"]), np.array(g["ops"], dtype=np.int8)
+        cmin = to_min_form(c, g["maximize"])
+        got = solver.solve_dense(A, b, cmin, ops, hist_cap=256)
+        ref = oracle.solve_lp(A, b, cmin, ops, hist_cap=256)
+        assert got["status"] == g["scipy_status"], k
+        assert got["status"] == ref["status"] and got["n_pivots"] == ref["n_pivots"], k
+        np.testing.assert_array_equal(got["piv_row"], ref["piv_row"])
+        np.testing.assert_array_equal(got["piv_col"], ref["piv_col"])
+        if got["status"] == 0:
+            assert_bit_equal(got["fun"], ref["fun"], f"mixed {k} fun")
+            assert_bit_equal(got["x"], ref["x"], f"mixed {k} x")
+            z = z_from_fun(got["fun"], g["maximize"])
+            assert abs(z - g["z"]) <= REL * max(1.0, abs(g["z"])), k
+
+
+# ---------------------------------------------------------------------------------------------------
+# BASELINE config 2 family: dense feasible LPs, Dantzig
+# ---------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("n", [16, 64, 128, 256])
+def test_dense_lp_exact_vs_oracle_and_golden(solver, oracle, golden, n):
+    A, b, c, ops, mx = W.dense_feasible_lp(n, seed=0)
+    cmin = to_min_form(c, mx)
+    cap = 1 << 14
+    got = solver.solve_dense(A, b, cmin, ops, native.make_opts(rule=native.RULE_DANTZIG), hist_cap=cap)
+    ref = oracle.solve_lp(A, b, cmin, ops, oracle.make_opts(rule=oracle.RULE_DANTZIG), hist_cap=cap)
+    assert got["status"] == 0 == ref["status"]
+    assert got["n_pivots"] == ref["n_pivots"]
+    np.testing.assert_array_equal(got["piv_row"], ref["piv_row"])
+    np.testing.assert_array_equal(got["piv_col"], ref["piv_col"])
+    assert_bit_equal(got["fun"], ref["fun"], "fun")
+    assert_bit_equal(got["x"], ref["x"], "x")
+    zg = golden["dense"][str(n)]["z"]
+    assert abs(-got["fun"] - zg) <= REL * abs(zg)
+
+
+def test_dense_1024_config2_vs_reference_golden(solver, golden):
+    """BASELINE config 2 at full size: z* within 1e-9 of the reference path (HiGHS) -- 447.0328820157."""
+    A, b, c, ops, mx = W.dense_feasible_lp(1024, seed=0)
+    got = solver.solve_dense(A, b, to_min_form(c, mx), ops, native.make_opts(rule=native.RULE_DANTZIG))
+    zg = golden["dense"]["1024"]["z"]
+    assert got["status"] == 0
+    assert abs(-got["fun"] - zg) <= REL * abs(zg)
+    x = got["x"]
+    assert (x >= -1e-9).all() and (A @ x <= b + 1e-7).all()
+    assert abs(c @ x - zg) <= 1e-8 * abs(zg)
+
+
+def test_dense_update_variants_agree(solver, oracle):
+    A, b, c, ops, mx = W.dense_feasible_lp(192, seed=5)
+    cmin = to_min_form(c, mx)
+    ref = oracle.solve_lp(A, b, cmin, ops, hist_cap=1 << 13)
+    for variant in (native.UPDATE_LDG, native.UPDATE_TMA):
+        for graph in (True, False):
+            got = solver.solve_dense(A, b, cmin, ops, native.make_opts(update_variant=variant, use_graph=graph,
+                                                                     check_every=16), hist_cap=1 << 13)
+            assert got["n_pivots"] == ref["n_pivots"], (variant, graph)
+            np.testing.assert_array_equal(got["piv_row"], ref["piv_row"])
+            assert_bit_equal(got["fun"], ref["fun"], f"variant {variant} graph {graph}")
+            assert_bit_equal(got["x"], ref["x"], f"variant {variant} graph {graph}")
+
+
+# ---------------------------------------------------------------------------------------------------
+# device-resident generated tableau (configs 4/5 generator), one phase at a time and as a loop
+# ---------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("shape", [(37, 53), (200, 300), (513, 1030)])
+def test_generated_tableau_and_single_phases_bit_exact(solver, oracle, shape):
+    m, n = shape
+    seed = 4
+    T, ld = _device_tableau(solver, m, 1, n + 1, n, n + m)
+    solver.generate(seed, n, 0)
+    ot = oracle.OracleTableau.generate(seed, m, n)
+    assert_bit_equal(solver.read_tableau(), ot.T, "generated tableau")
+    rl, cl = solver.get_labels()
+    np.testing.assert_array_equal(rl, ot.rowlab)
+    np.testing.assert_array_equal(cl, ot.collab)
+    for it in range(6):
+        rule = native.RULE_BLAND if it % 2 else native.RULE_DANTZIG
+        s = solver.select_entering(rule=rule)
+        assert s == ot.price(rule=rule)
+        r = solver.ratio_test(s)
+        col = ot.extract_col(s)
+        assert r == ot.ratio(col)
+        variant = native.UPDATE_TMA if it % 3 == 2 else native.UPDATE_LDG
+        solver.pivot(r, s, variant)
+        ot.pivot(r, s)
+        assert_bit_equal(solver.read_tableau(), ot.T, f"tableau after pivot {it}")
+        rl, cl = solver.get_labels()
+        np.testing.assert_array_equal(rl, ot.rowlab)
+        np.testing.assert_array_equal(cl, ot.collab)
+
+
+@pytest.mark.parametrize("variant", [native.UPDATE_LDG, native.UPDATE_TMA])
+@pytest.mark.parametrize("rule", [native.RULE_BLAND, native.RULE_DANTZIG])
+def test_device_loop_fixed_budget_bit_exact(solver, oracle, rule, variant):
+    """Config 4 in miniature: a fixed pivot budget on a generated square tableau, Bland and Dantzig."""
+    m, n, budget = 255, 255, 150
+    T, ld = _device_tableau(solver, m, 1, n + 1, n, n + m)
+    solver.generate(4, n, 0)
+    got = solver.run(native.make_opts(rule=rule, max_pivots=budget, update_variant=variant), hist_cap=budget)
+    ot = oracle.OracleTableau.generate(4, m, n)
+    ref = ot.solve(oracle.make_opts(rule=rule, max_pivots=budget), hist_cap=budget)
+    assert got["status"] == ref["status"] == 1 and got["n_pivots"] == ref["n_pivots"] == budget
+    np.testing.assert_array_equal(got["piv_row"], ref["piv_row"])
+    np.testing.assert_array_equal(got["piv_col"], ref["piv_col"])
+    np.testing.assert_array_equal(got["enter_lab"], ref["enter_lab"])
+    np.testing.assert_array_equal(got["leave_lab"], ref["leave_lab"])
+    assert_bit_equal(solver.read_tableau(), ot.T, "tableau after the budget")
+    assert_bit_equal(got["fun"], ref["fun"], "fun")
+
+
+def test_device_loop_to_optimality(solver, oracle):
+    m, n = 96, 160
+    T, ld = _device_tableau(solver, m, 1, n + 1, n, n + m)
+    solver.generate(11, n, 0)
+    got = solver.run(native.make_opts(rule=native.RULE_DANTZIG), hist_cap=1 << 13)
+    ot = oracle.OracleTableau.generate(11, m, n)
+    ref = ot.solve(oracle.make_opts(rule=oracle.RULE_DANTZIG), hist_cap=1 << 13)
+    assert got["status"] == ref["status"] == 0
+    assert got["n_pivots"] == ref["n_pivots"]
+    np.testing.assert_array_equal(got["piv_row"], ref["piv_row"])
+    assert_bit_equal(got["x"], ot.read_x(), "x")
+    assert_bit_equal(solver.read_tableau(), ot.T, "final tableau")
+
+
+def test_config4_full_size_properties(solver):
+    """BASELINE config 4 at full size (16384 x 16384, Bland): size-independent properties of a pivot.
+    After pivoting on (r, s): column s holds -col/p (1/p at row r), row r holds row/p, the objective value
+    moved by -d_s * rhs_r / p, the basis swap is recorded, and the next Bland choice is deterministic."""
+    torch = _torch()
+    m = n = 16383
+    T, ld = _device_tableau(solver, m, 1, n + 1, n, n + m)
+    solver.generate(4, n, 0)
+    Tt = T.view(m + 1, ld)
+    s = solver.select_entering(rule=native.RULE_BLAND)
+    assert s == 0  # every reduced cost is negative at the start: Bland takes variable 0
+    r = solver.ratio_test(s)
+    col = Tt[:, s].clone()
+    rowr = Tt[r, : n + 1].clone()
+    rhs = Tt[:, n].clone()
+    ratios = torch.where(col[:m] > 1e-9, rhs[:m] / col[:m], torch.full_like(col[:m], float("inf")))
+    assert int(torch.argmin(ratios)) == r
+    p = col[r].item()
+    z0 = Tt[m, n].item()
+    some = Tt[5:9, 7:11].clone()
+    solver.pivot(r, s, native.UPDATE_AUTO)
+    torch.cuda.synchronize()
+    inv_p = 1.0 / p
+    exp_col = -(col * inv_p)
+    exp_col[r] = inv_p
+    assert torch.equal(Tt[:, s], exp_col)
+    exp_row = rowr / p
+    exp_row[s] = inv_p
+    assert torch.equal(Tt[r, : n + 1], exp_row)
+    q = rowr[7:11] / p
+    exp_some = torch.stack([torch.addcmul(some[k], -col[5 + k], q) for k in range(4)])  # not fused: 1 ulp slack
+    assert torch.allclose(Tt[5:9, 7:11], exp_some, rtol=1e-15, atol=1e-15)
+    zexp = z0 - col[m].item() * (rhs[r].item() / p)
+    assert abs(Tt[m, n].item() - zexp) <= 1e-12 * max(1.0, abs(zexp))
+    rl, cl = solver.get_labels()
+    assert rl[r] == 0 and cl[s] == n + r
+    # a short Bland loop keeps the objective monotone (maximisation form: -T[m][n] decreases)
+    fun_before = -Tt[m, n].item()
+    res = solver.run(native.make_opts(rule=native.RULE_BLAND, max_pivots=8), hist_cap=8)
+    assert res["n_pivots"] == 8 and res["status"] == 1
+    assert res["fun"] <= fun_before + 1e-9 * abs(fun_before)
+    assert (np.diff(res["enter_lab"]) != 0).all()
+    del T
+
+
+# ---------------------------------------------------------------------------------------------------
+# BASELINE config 3: batched small LPs
+# ---------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("rule", [native.RULE_DANTZIG, native.RULE_BLAND])
+def test_batched_bit_exact_vs_oracle(solver, oracle, rule):
+    A, b, c, ops = W.batched_small_lps(0, 1000)
+    got = solver.solve_batched(A, b, c, ops, native.make_opts(rule=rule), log_cap=96)
+    ref = oracle.solve_batched(A, b, c, ops, oracle.make_opts(rule=rule), log_cap=96, threads=8)
+    np.testing.assert_array_equal(got["status"], ref["status"])
+    np.testing.assert_array_equal(got["n_pivots"], ref["n_pivots"])
+    np.testing.assert_array_equal(got["piv_log"], ref["piv_log"])
+    ok = got["status"] == 0
+    assert_bit_equal(got["fun"][ok], ref["fun"][ok], "fun")
+    assert_bit_equal(got["x"][ok], ref["x"][ok], "x")
+    assert set(np.unique(got["status"])) == {0, 2, 3}
+
+
+def test_batched_against_reference_golden(solver, golden):
+    g = golden["batched"]
+    A, b, c, ops = W.batched_small_lps(0, g["count"], g["m"], g["n"], g["base_seed"])
+    got = solver.solve_batched(A, b, c, ops)
+    for k, row in enumerate(g["results"]):
+        assert got["status"][k] == row["scipy_status"], k
+        if row["z"] is not None:
+            assert abs(got["fun"][k] - row["z"]) <= REL * max(1.0, abs(row["z"])), k
+
+
+@pytest.mark.parametrize("shape", [(1, 1), (3, 2), (7, 12), (33, 40), (64, 64)])
+def test_batched_ragged_shapes(solver, oracle, shape):
+    m, n = shape
+    A, b, c, ops = W.batched_small_lps(0, 257, m, n, base_seed=9)
+    got = solver.solve_batched(A, b, c, ops, log_cap=32)
+    ref = oracle.solve_batched(A, b, c, ops, log_cap=32, threads=8)
+    np.testing.assert_array_equal(got["status"], ref["status"])
+    np.testing.assert_array_equal(got["n_pivots"], ref["n_pivots"])
+    np.testing.assert_array_equal(got["piv_log"], ref["piv_log"])
+    ok = got["status"] == 0
+    assert_bit_equal(got["fun"][ok], ref["fun"][ok], "fun")
+    assert_bit_equal(got["x"][ok], ref["x"][ok], "x")
+
+
+def test_batched_matches_single_lp_path(solver):
+    """The warp-per-LP kernel and the multi-kernel single-LP path take the same pivots."""
+    A, b, c, ops = W.batched_small_lps(0, 40)
+    got = solver.solve_batched(A, b, c, ops, log_cap=96)
+    for k in range(40):
+        one = solver.solve_dense(A[k], b[k], c[k], ops[k], hist_cap=96)
+        assert one["status"] == got["status"][k]
+        assert one["n_pivots"] == got["n_pivots"][k]
+        np.testing.assert_array_equal(one["piv_row"], got["piv_log"][k, : one["n_pivots"], 0])
+        np.testing.assert_array_equal(one["piv_col"], got["piv_log"][k, : one["n_pivots"], 1])
+        if one["status"] == 0:
+            assert_bit_equal(one["fun"], got["fun"][k], "fun")
+            assert_bit_equal(one["x"], got["x"][k], "x")
+
+
+# ---------------------------------------------------------------------------------------------------
+# edge cases
+# ---------------------------------------------------------------------------------------------------
+def test_empty_constraint_set_is_unbounded_or_trivial(solver):
+    # K7: no constraints, max x1+x2  -> unbounded (status 3 -> "Error" in the reference's mapping)
+    got = solver.solve_dense(np.zeros((0, 2)), np.zeros(0), np.array([-1.0, -1.0]), np.zeros(0, dtype=np.int8))
+    assert got["status"] == native.STATUS_UNBOUNDED
+    # no constraints, min x1+x2 -> optimal at 0
+    got = solver.solve_dense(np.zeros((0, 2)), np.zeros(0), np.array([1.0, 1.0]), np.zeros(0, dtype=np.int8))
+    assert got["status"] == 0 and got["fun"] == 0.0 and (got["x"] == 0).all()
+
+
+def test_pivot_limit_status(solver):
+    A, b, c, ops, mx = W.dense_feasible_lp(64, seed=1)
+    got = solver.solve_dense(A, b, to_min_form(c, mx), ops, native.make_opts(max_pivots=5), hist_cap=16)
+    assert got["status"] == native.STATUS_LIMIT and got["n_pivots"] == 5
+
+
+def test_redundant_equalities_and_degenerate_rows(solver, oracle):
+    # duplicated equality rows leave an artificial basic at level zero: exercises the drive-out path
+    A = np.array([[1.0, 1.0, 0.0], [1.0, 1.0, 0.0], [2.0, 2.0, 0.0], [0.0, 1.0, 1.0]])
+    b = np.array([4.0, 4.0, 8.0, 3.0])
+    ops = np.array([2, 2, 2, 0], dtype=np.int8)
+    c = np.array([1.0, 2.0, -1.0])
+    got = solver.solve_dense(A, b, c, ops, hist_cap=32)
+    ref = oracle.solve_lp(A, b, c, ops, hist_cap=32)
+    assert got["status"] == ref["status"] == 0
+    assert got["n_pivots"] == ref["n_pivots"]
+    np.testing.assert_array_equal(got["piv_row"], ref["piv_row"])
+    np.testing.assert_array_equal(got["piv_col"], ref["piv_col"])
+    assert_bit_equal(got["fun"], ref["fun"], "fun")
+    assert_bit_equal(got["x"], ref["x"], "x")
+
+
+def test_invalid_arguments_fail_loudly(solver):
+    with pytest.raises(native.B200LPError):
+        solver.solve_dense(np.zeros((1, 1)), np.zeros(1), np.zeros(1), np.array([7], dtype=np.int8))
+    with pytest.raises(native.B200LPError):
+        solver.solve_dense(np.zeros((1, 1)), np.zeros(1), np.zeros(1), np.zeros(1, dtype=np.int8),
+                           native.make_opts(rule=9))
