@@ -1,0 +1,502 @@
+#!/usr/bin/env python
+"""bench.py -- the simplex tableau pivot loop on B200 (BASELINE.json metric: pivots/s and pivot-update HBM GB/s).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--pivots P]
+
+A "step" is one pass of the hot path over one batch of synthetic input: P pivots of the device-resident loop.
+  N = 1 : BASELINE config 4 -- one dense 16384 x 16384 fp64 tableau (2.1 GB > L2), Bland rule, fixed budget.
+  N > 1 : BASELINE config 5 -- one dense 131072 x 131072 fp64 tableau (137 GB) column-sharded over the N GPUs,
+          one all-gather of candidate columns per pivot (launched by torchrun, one rank per GPU).
+`value`   = pivots/s of the whole job with the tableau already resident in HBM (max over ranks, CUDA events).
+`e2e`     = the same metric through the reference-facing C-ABI call with HOST buffers (b200lp_solve_dense from
+            pinned host arrays A, b, c -> x, z), host<->device copies inside the timed region.
+`roofline`= pivot-update kernel: algorithmic bytes per launch (2*R*C*8) / its average duration, measured live with
+            CUDA events around every launch of a real loop; peak = MEASURED_PEAKS.json hbm_gbs (else the fallback).
+`cpu_baseline` = oracle/ (the CPU restatement, OpenMP) timed on this box's host cores on a bounded sample.
+`--impl reference` times that CPU path alone as the reference arm (the reference itself holds no pivot loop:
+its engine is the un-vendored simple-simplex package).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+FALLBACK_HBM_GBS = 6650.0  # /opt/skills/guides/B200_PROFILING.md
+
+
+def measured_peak():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return FALLBACK_HBM_GBS, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index=0):
+        self.gpu = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(self.gpu)],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 8:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ----------------------------------------------------------------------------------------------------------
+# CPU arm: the oracle port on the host cores
+# ----------------------------------------------------------------------------------------------------------
+def cpu_pivots_per_s(R, C_total, rule, pivots, seed, threads=None, repeats=1):
+    """Oracle (OpenMP) on a generated R x C_total tableau: (pivots/s, threads, seconds)."""
+    from oracle import oracle as O
+    O.build()
+    threads = threads or O.max_threads()
+    t = O.OracleTableau.generate(seed, R - 1, C_total - 1)
+    best = None
+    for _ in range(repeats):
+        t0 = time.perf_counter()
+        res = t.solve(O.make_opts(rule=rule, max_pivots=pivots, threads=threads))
+        dt = time.perf_counter() - t0
+        pps = res["n_pivots"] / dt
+        best = pps if best is None else max(best, pps)
+    return best, threads, dt
+
+
+def run_reference_arm(args):
+    """--impl reference: the CPU implementation of the path on this box's host cores, same config/metric/unit."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    R = args.rows
+    C = args.rows if args.gpus == 1 else args.rows  # the CPU arm always times a square slab of the config's row count
+    sample_rows = R
+    note = f"{args.ref_pivots} pivots per step on the full {R} x {C} tableau"
+    if args.gpus > 1:
+        # config 5 does not fit host-side timing budgets: time a 16384-column slab and scale by columns (extrapolated)
+        C = 16384
+        note = (f"{args.ref_pivots} pivots per step on a {R} x {C} column slab of the {R} x {args.cols_total} tableau, "
+                f"scaled by {C}/{args.cols_total} (extrapolated)")
+    from oracle import oracle as O
+    O.build()
+    threads = O.max_threads()
+    rule = 1 if args.rule == "bland" else 0
+    tab = O.OracleTableau.generate(args.seed, sample_rows - 1, C - 1)
+    opts = O.make_opts(rule=rule, max_pivots=args.ref_pivots, threads=threads)
+    for _ in range(args.warmup):
+        tab.solve(opts)
+    t0 = time.perf_counter()
+    n = 0
+    for _ in range(args.steps):
+        n += tab.solve(opts)["n_pivots"]
+    dt = time.perf_counter() - t0
+    pps = n / dt
+    if args.gpus > 1:
+        pps *= C / args.cols_total
+    line = {
+        "impl": "reference", "metric": "pivots_per_s", "value": pps, "unit": "pivots/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True,
+        "scaling": "strong" if args.gpus > 1 else "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": workload_config(args),
+        "cpu_baseline": {"value": pps, "unit": "pivots/s", "cores": threads, "kind": "port", "sample": note,
+                         "host_cpus": os.cpu_count()},
+        "e2e": {"value": pps, "unit": "pivots/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+def workload_config(args):
+    if args.gpus == 1:
+        return {"workload": f"BASELINE config 4: single dense {args.rows}x{args.rows} fp64 condensed tableau, "
+                            f"{args.rule} rule, fixed budget of {args.pivots} pivots per step",
+                "rows": args.rows, "cols": args.rows, "rule": args.rule, "pivots_per_step": args.pivots,
+                "bytes_per_pivot": 16 * args.rows * args.rows, "l2": "tableau (2.1 GB) is larger than L2 (126 MB)",
+                "parallelism": "1 GPU"}
+    return {"workload": f"BASELINE config 5: single dense {args.rows}x{args.cols_total} fp64 condensed tableau "
+                        f"column-sharded over {args.gpus} GPUs, {args.rule} rule, {args.pivots} pivots per step",
+            "rows": args.rows, "cols": args.cols_total, "rule": args.rule, "pivots_per_step": args.pivots,
+            "bytes_per_pivot": 16 * args.rows * args.cols_total,
+            "l2": "each shard is far larger than L2", "parallelism": f"column-sharded x{args.gpus}, "
+            "1 all-gather of candidate columns per pivot"}
+
+
+# ----------------------------------------------------------------------------------------------------------
+# GPU arm
+# ----------------------------------------------------------------------------------------------------------
+def bench_single_gpu(args):
+    import torch
+    from simplex_solver_b200 import native
+
+    torch.cuda.set_device(0)
+    R = args.rows
+    m = n = R - 1
+    C = ld = R
+    rule = native.RULE_BLAND if args.rule == "bland" else native.RULE_DANTZIG
+    variant = {"auto": native.UPDATE_AUTO, "ldg": native.UPDATE_LDG, "tma": native.UPDATE_TMA}[args.variant]
+    s = native.Solver(0)
+    s.set_stream(torch.cuda.current_stream().cuda_stream)
+    T = torch.empty(R * ld, dtype=torch.float64, device="cuda:0")
+    s.attach(T.data_ptr(), m, 1, C, ld, n, n + m, keep=T)
+    s.generate(args.seed, n, 0)
+    torch.cuda.synchronize()
+    opts = native.make_opts(rule=rule, max_pivots=args.pivots, update_variant=variant)
+    bytes_per_pivot = 16.0 * R * C
+
+    launches = 0
+    for _ in range(args.warmup):
+        s.run(opts)
+    torch.cuda.synchronize()
+    sampler = ClockSampler(0)
+    sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    pivots = 0
+    for _ in range(args.steps):
+        r = s.run(opts)
+        pivots += r["n_pivots"]
+        launches += r["kernel_launches"]
+    ev1.record()
+    torch.cuda.synchronize()
+    clocks = sampler.stop()
+    sec = ev0.elapsed_time(ev1) * 1e-3
+    value = pivots / sec
+
+    # live per-kernel durations of a real loop (events around every launch)
+    prof = s.profile_loop(opts, iters=min(64, args.pivots))
+    peak, peak_src = measured_peak()
+    achieved = bytes_per_pivot / (prof["update_ms"] * 1e-3) / 1e9
+    ncu_traffic = None
+    try:
+        with open(os.path.join(ROOT, "profiles", "update_kernel_traffic.json")) as f:
+            ncu_traffic = json.load(f).get("dram_bytes_per_launch")
+    except Exception:
+        pass
+    roofline = {"bound": "hbm", "kernel": "k_update_ldg<256,8>" if variant != native.UPDATE_TMA else "k_update_tma",
+                "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "peak_source": peak_src,
+                "frac_of_nominal_8TBs": achieved / 8000.0, "traffic": ncu_traffic,
+                "algorithmic_bytes_per_launch": bytes_per_pivot,
+                "kernel_ms": {"update": prof["update_ms"], "price": prof["price_ms"], "ratio": prof["ratio_ms"]},
+                "update_share_of_pivot": prof["update_ms"] / (prof["update_ms"] + prof["price_ms"] + prof["ratio_ms"]),
+                "loop_GBps": value * bytes_per_pivot / 1e9, "loop_frac_of_peak": value * bytes_per_pivot / 1e9 / peak,
+                "loop_frac_of_nominal_8TBs": value * bytes_per_pivot / 1e9 / 8000.0}
+
+    # ---- e2e: the reference-facing call with HOST buffers (pinned), copies inside the timed region ----
+    s.generate(args.seed, n, 0)
+    torch.cuda.synchronize()
+    Th = torch.empty((R, ld), dtype=torch.float64, pin_memory=True)
+    Th.copy_(T.view(R, ld))
+    torch.cuda.synchronize()
+    A_h = Th[:m, :n]                      # row stride ld: passed as lda
+    b_h = Th[:m, n].clone().pin_memory()
+    c_h = Th[m, :n].clone().pin_memory()  # objective row = costs of the minimisation form
+    ops_h = np.zeros(m, dtype=np.int8)
+    s2 = native.Solver(0)
+    s2.set_stream(torch.cuda.current_stream().cuda_stream)
+    del T
+    s.close()
+    torch.cuda.empty_cache()
+
+    def e2e_step():
+        return _solve_dense_host_ptr(s2, A_h, b_h, c_h, ops_h, opts, m, n, ld)
+
+    e2e_step()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e2e_steps = max(1, min(args.steps, 3))
+    e0.record()
+    piv2 = 0
+    for _ in range(e2e_steps):
+        r = e2e_step()
+        piv2 += r["n_pivots"]
+    e1.record()
+    torch.cuda.synchronize()
+    e2e_sec = e0.elapsed_time(e1) * 1e-3
+    e2e = {"value": piv2 / e2e_sec, "unit": "pivots/s", "h2d_bytes_per_step": int(8 * (m * n + m + n)),
+           "d2h_bytes_per_step": int(8 * (n + 1) + 128), "steps": e2e_steps, "ms_per_step": e2e_sec / e2e_steps * 1e3,
+           "call": "b200lp_solve_dense(A, b, c, ops from pinned host memory) -> x, c'x on the host"}
+    s2.close()
+    del Th
+    torch.cuda.empty_cache()
+
+    # ---- CPU baseline on the host cores (bounded sample) ----
+    cpu = None
+    if not args.no_cpu:
+        cpu_piv = args.cpu_pivots
+        pps, threads, dt = cpu_pivots_per_s(R, C, 1 if args.rule == "bland" else 0, cpu_piv, args.seed)
+        cpu = {"value": pps, "unit": "pivots/s", "cores": threads, "kind": "port", "host_cpus": os.cpu_count(),
+               "sample": f"{cpu_piv} pivots of the same {R}x{C} tableau with oracle/ (OpenMP), {dt:.1f} s"}
+
+    line = {
+        "metric": "pivots_per_s", "value": value, "unit": "pivots/s", "n_gpus": 1, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": sec / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": workload_config(args),
+        "hbm_GBps": value * bytes_per_pivot / 1e9, "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
+        "gpu_launches": int(launches), "clocks": clocks,
+    }
+    if args.secondary:
+        line["secondary"] = secondary_configs(args)
+    print(json.dumps(line))
+
+
+def _solve_dense_host_ptr(solver, A_h, b_h, c_h, ops_h, opts, m, n, lda):
+    """solve_dense on pinned torch host tensors without an extra numpy copy."""
+    import ctypes as C
+    from simplex_solver_b200 import native
+    p = native.Problem(m, n, lda, C.c_void_p(A_h.data_ptr()), C.c_void_p(b_h.data_ptr()), C.c_void_p(c_h.data_ptr()),
+                       ops_h.ctypes.data_as(C.c_void_p), 0, 0)
+    res, keep = native.Solver._result(n, 0)
+    native.check(native.lib().b200lp_solve_dense(solver._h, C.byref(p), C.byref(opts), C.byref(res)))
+    return native.Solver._result_dict(res, keep, n)
+
+
+def secondary_configs(args):
+    """BASELINE configs 2 and 3 on this GPU next to the reference CPU path (scipy HiGHS, as solver_controller.py:78-85)."""
+    import torch
+    from simplex_solver_b200 import native, workloads as W
+    out = {}
+    s = native.Solver(0)
+    # config 2: dense 1024 x 1024, Dantzig, end to end from host arrays
+    A, b, c, ops, mx = W.dense_feasible_lp(1024, 0)
+    cmin = -c
+    s.solve_dense(A, b, cmin, ops)
+    t0 = time.perf_counter()
+    r = s.solve_dense(A, b, cmin, ops)
+    gpu_s = time.perf_counter() - t0
+    c2 = {"gpu_e2e_s": gpu_s, "gpu_device_ms": r["device_ms"], "pivots": r["n_pivots"], "z": -r["fun"],
+          "pivots_per_s": r["n_pivots"] / (r["device_ms"] * 1e-3), "us_per_pivot": r["device_ms"] * 1e3 / r["n_pivots"]}
+    try:
+        from scipy.optimize import linprog
+        t0 = time.perf_counter()
+        ref = linprog(cmin, A_ub=A, b_ub=b, bounds=[(0, None)] * 1024, method="highs-ds",
+                      options={"presolve": True, "time_limit": 10})
+        c2.update(reference_highs_s=time.perf_counter() - t0, reference_z=-ref.fun, reference_nit=int(ref.nit),
+                  z_rel_err=abs(-r["fun"] + ref.fun) / abs(ref.fun), speedup_e2e=(time.perf_counter() - t0) / gpu_s,
+                  reference_cores=1)
+    except Exception as e:
+        c2["reference_highs_s"] = f"unavailable: {e}"
+    out["config2_dense1024_dantzig"] = c2
+    # config 3: 100k x (20 x 30) batched (one GPU's view: the whole batch)
+    B = args.batch
+    Ab, bb, cb, ob = W.batched_small_lps(0, B)
+    s.solve_batched(Ab[:1000], bb[:1000], cb[:1000], ob[:1000])
+    t0 = time.perf_counter()
+    rb = s.solve_batched(Ab, bb, cb, ob, want_x=True)
+    wall = time.perf_counter() - t0
+    c3 = {"batch": B, "kernel_ms": rb["device_ms"], "LPs_per_s_kernel": B / (rb["device_ms"] * 1e-3),
+          "LPs_per_s_e2e_pageable_host": B / wall, "pivots": int(rb["n_pivots"].sum()),
+          "pivots_per_s_kernel": float(rb["n_pivots"].sum()) / (rb["device_ms"] * 1e-3),
+          "status_counts": {int(k): int(v) for k, v in zip(*np.unique(rb["status"], return_counts=True))}}
+    try:
+        from scipy.optimize import linprog
+        k = 200
+        t0 = time.perf_counter()
+        agree = 0
+        for i in range(k):
+            A_ub = np.vstack([Ab[i][ob[i] == 0], -Ab[i][ob[i] == 1]])
+            b_ub = np.concatenate([bb[i][ob[i] == 0], -bb[i][ob[i] == 1]])
+            A_eq = Ab[i][ob[i] == 2]
+            b_eq = bb[i][ob[i] == 2]
+            ref = linprog(cb[i], A_ub=A_ub if len(b_ub) else None, b_ub=b_ub if len(b_ub) else None,
+                          A_eq=A_eq if len(b_eq) else None, b_eq=b_eq if len(b_eq) else None,
+                          bounds=[(0, None)] * Ab.shape[2], method="highs-ds", options={"presolve": True, "time_limit": 10})
+            same = int(ref.status) == int(rb["status"][i])
+            if same and ref.status == 0:
+                same = abs(ref.fun - rb["fun"][i]) <= 1e-9 * max(1.0, abs(ref.fun))
+            agree += bool(same)
+        dt = time.perf_counter() - t0
+        c3.update(reference_highs_LPs_per_s_1core=k / dt, reference_sample=k, reference_agree=agree)
+    except Exception as e:
+        c3["reference_highs_LPs_per_s_1core"] = f"unavailable: {e}"
+    out["config3_batched_20x30"] = c3
+    s.close()
+    torch.cuda.empty_cache()
+    return out
+
+
+def bench_sharded(args):
+    import torch
+    import torch.distributed as dist
+    from simplex_solver_b200 import native
+    from simplex_solver_b200.sharded import CudaShardEngine, ShardedTableau
+
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", str(rank)))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
+    R = args.rows
+    m = R - 1
+    c_loc = args.cols_total // world            # stored columns per shard, RHS replica included
+    ncols = c_loc - 1
+    n_total = world * ncols
+    rule = native.RULE_BLAND if args.rule == "bland" else native.RULE_DANTZIG
+    opts = native.make_opts(rule=rule, max_pivots=args.pivots)
+
+    def make_engine():
+        return CudaShardEngine(m, n_total, rank * ncols, ncols, args.seed, device=local)
+
+    eng = make_engine()
+    drv = ShardedTableau(eng, world, rank)
+    torch.cuda.synchronize()
+    for _ in range(args.warmup):
+        drv.run(opts, args.pivots, check_every=args.pivots)
+    torch.cuda.synchronize()
+    dist.barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    pivots = 0
+    for _ in range(args.steps):
+        _, done_now = drv.run(opts, args.pivots, check_every=args.pivots)
+        pivots += done_now
+    ev1.record()
+    torch.cuda.synchronize()
+    dist.barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    t = torch.tensor([ev0.elapsed_time(ev1) * 1e-3], dtype=torch.float64, device=f"cuda:{local}")
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    sec = float(t.item())
+    value = pivots / sec
+    bytes_per_pivot = 16.0 * R * args.cols_total
+
+    # roofline of the update kernel on this shard, timed alone on the launching stream
+    upd_ms = eng.solver.time_update(1, 1, native.UPDATE_AUTO, 5)
+    shard_bytes = 16.0 * R * c_loc
+    peak, peak_src = measured_peak()
+    tt = torch.tensor([upd_ms], dtype=torch.float64, device=f"cuda:{local}")
+    dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    upd_ms = float(tt.item())
+    achieved = shard_bytes / (upd_ms * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "kernel": "k_update_ldg<256,8> (per shard)", "achieved": achieved, "peak": peak,
+                "unit": "GB/s", "frac": achieved / peak, "peak_source": peak_src, "traffic": None,
+                "algorithmic_bytes_per_launch": shard_bytes, "kernel_ms": {"update": upd_ms},
+                "loop_GBps_aggregate": value * bytes_per_pivot / 1e9,
+                "loop_frac_of_peak_per_gpu": value * bytes_per_pivot / 1e9 / world / peak,
+                "loop_frac_of_nominal_8TBs_per_gpu": value * bytes_per_pivot / 1e9 / world / 8000.0}
+
+    # e2e: inputs of this config cannot be staged through the host (137 GB); the end-to-end pass regenerates the
+    # shard on the device inside the timed region and reads x*, z back to the host.
+    del drv
+    del eng
+    torch.cuda.empty_cache()
+    dist.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    eng = make_engine()
+    drv = ShardedTableau(eng, world, rank)
+    _, nq = drv.run(opts, args.pivots, check_every=args.pivots)
+    x, fun = eng.solution()
+    e1.record()
+    torch.cuda.synchronize()
+    t2 = torch.tensor([e0.elapsed_time(e1) * 1e-3], dtype=torch.float64, device=f"cuda:{local}")
+    dist.all_reduce(t2, op=dist.ReduceOp.MAX)
+    e2e = {"value": nq / float(t2.item()), "unit": "pivots/s", "h2d_bytes_per_step": 0,
+           "d2h_bytes_per_step": int(8 * (n_total + 1)),
+           "note": "inputs generated on the device inside the timed region: a 137 GB tableau cannot be staged "
+                   "through host memory (SURVEY.md 8d); x*, z are read back to the host"}
+    launches = args.steps * args.pivots * 5
+    if rank == 0:
+        line = {
+            "metric": "pivots_per_s", "value": value, "unit": "pivots/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": sec / args.steps * 1e3, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": workload_config(args), "hbm_GBps": value * bytes_per_pivot / 1e9, "roofline": roofline,
+            "cpu_baseline": None, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
+            "collective": {"op": "all_gather_into_tensor (NCCL)", "bytes_per_rank_per_pivot": 8 * (R + 2)},
+        }
+        print(json.dumps(line))
+    dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--pivots", type=int, default=None, help="pivots per step")
+    ap.add_argument("--rows", type=int, default=None)
+    ap.add_argument("--cols-total", type=int, default=None)
+    ap.add_argument("--rule", default="bland", choices=["bland", "dantzig"])
+    ap.add_argument("--variant", default="auto", choices=["auto", "ldg", "tma"])
+    ap.add_argument("--seed", type=int, default=4)
+    ap.add_argument("--batch", type=int, default=100000)
+    ap.add_argument("--ref-pivots", type=int, default=8, help="pivots per step of the CPU reference arm")
+    ap.add_argument("--cpu-pivots", type=int, default=48, help="pivots of the cpu_baseline sample")
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-secondary", dest="secondary", action="store_false")
+    args = ap.parse_args()
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if world > 1:
+        args.gpus = world
+    if args.gpus == 1:
+        args.rows = args.rows or 16384
+        args.cols_total = args.rows
+        args.pivots = args.pivots or 128
+    else:
+        args.rows = args.rows or 131072
+        args.cols_total = args.cols_total or 131072
+        args.pivots = args.pivots or 16
+    if args.impl == "reference":
+        run_reference_arm(args)
+        return
+    if args.gpus == 1:
+        bench_single_gpu(args)
+    else:
+        bench_sharded(args)
+
+
+if __name__ == "__main__":
+    main()

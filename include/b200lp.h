@@ -119,6 +119,13 @@ int b200lp_synchronize(b200lp_solver *s);
 
 /* ---- one LP, reference-facing (linprog seam) --------------------------------------------------------- */
 int b200lp_solve_dense(b200lp_solver *s, const b200lp_problem *p, const b200lp_opts *o, b200lp_result *r);
+/* the two halves of b200lp_solve_dense: build the initial tableau in the solver's own device buffer (then
+ * b200lp_dims / b200lp_get_labels / b200lp_read_tableau describe it), and b200lp_solve below.            */
+int b200lp_build_dense(b200lp_solver *s, const b200lp_problem *p);
+/* keep a dense R x C copy of the tableau after each of the first `cap` pivots of the following solves in the
+ * caller-owned DEVICE buffer snaps_dev (cap * R * C doubles); NULL switches it off.  Feeds the "pivotSteps"
+ * of solver_controller.py:332-362 for small LPs.                                                          */
+int b200lp_set_snapshots(b200lp_solver *s, double *snaps_dev, int64_t cap);
 
 /* ---- device-resident tableau ------------------------------------------------------------------------ */
 /* Stored (condensed) tableau: R = m + n_obj rows, C columns, last column = right-hand side, row stride ld
@@ -171,6 +178,11 @@ int b200lp_solve_batched(b200lp_solver *s, int64_t B, int64_t m, int64_t n, cons
  * (CUDA events on the solver's stream); the tableau is modified.                                        */
 int b200lp_time_update(b200lp_solver *s, int64_t row, int64_t col, int32_t update_variant, int32_t reps,
                        double *ms_per_launch);
+
+/* `iters` loop iterations with plain launches and CUDA events around every kernel: average duration of the
+ * price, ratio and update kernels in their real order (what bench.py reports under "roofline").            */
+int b200lp_profile_loop(b200lp_solver *s, const b200lp_opts *o, int64_t obj_row, int32_t iters, double *ms_price,
+                        double *ms_ratio, double *ms_update, int64_t *pivots_done);
 
 #ifdef __cplusplus
 }

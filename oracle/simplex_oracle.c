@@ -136,6 +136,9 @@ ORC_EXPORT int orc_generate(orc_tableau *t, uint64_t seed, int64_t m, int64_t n_
     if (orc_alloc(t, m, 1, ncols + 1, ld)) return -1;
     t->n_struct = n_total;
     t->art_base = (int32_t)(n_total + m);
+#ifdef _OPENMP
+#pragma omp parallel for schedule(static)
+#endif
     for (int64_t i = 0; i < t->R; ++i) {
         double *row = t->T + i * t->ld;
         for (int64_t j = 0; j < ncols; ++j) row[j] = orc_gen_entry(seed, m, n_total, i, lab0 + j);

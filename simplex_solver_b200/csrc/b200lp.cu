@@ -85,8 +85,10 @@ struct GraphKey {
     int32_t rule = -1, variant = -1, iters = 0;
     double eps_cost = 0, eps_pivot = 0;
     int64_t hist_cap = 0;
+    const double* snaps = nullptr;
+    int64_t snap_cap = 0;
     bool operator==(const GraphKey& o) const {
-        return T == o.T && R == o.R && C == o.C && ld == o.ld && obj_row == o.obj_row && rule == o.rule &&
+        return snaps == o.snaps && snap_cap == o.snap_cap && T == o.T && R == o.R && C == o.C && ld == o.ld && obj_row == o.obj_row && rule == o.rule &&
                variant == o.variant && iters == o.iters && eps_cost == o.eps_cost && eps_pivot == o.eps_pivot &&
                hist_cap == o.hist_cap;
     }
@@ -123,6 +125,10 @@ struct b200lp_solver {
     CUtensorMap tmap;
     const double* tmap_T = nullptr;
     int64_t tmap_R = 0, tmap_C = 0, tmap_ld = 0;
+
+    // optional dense copy of the tableau after every pivot (caller-owned device buffer)
+    double* snaps = nullptr;
+    int64_t snap_cap = 0;
 
     cudaGraphExec_t graph = nullptr;
     GraphKey graph_key;
@@ -445,11 +451,21 @@ static int launch_reset(b200lp_solver* s, int64_t max_pivots, bool keep_count) {
     return 0;
 }
 
+static int launch_snapshot(b200lp_solver* s) {
+    if (!s->snaps) return 0;
+    const int blocks = clampi((s->R * s->C + 255) / 256, 1, 4 * s->sm_count);
+    k_snapshot<<<blocks, 256, 0, s->stream>>>(s->T, s->R, s->C, s->ld, s->st.p, s->snaps, s->snap_cap);
+    s->launches++;
+    CK(cudaGetLastError());
+    return 0;
+}
+
 // one iteration of the loop on the stream
 static int enqueue_iteration(b200lp_solver* s, const b200lp_opts* o, int64_t obj_row) {
     CKR(launch_price(s, obj_row, o->rule, o->eps_cost, false));
     CKR(launch_ratio(s, o->eps_pivot, false, nullptr, 0));
     CKR(launch_update(s, o->update_variant));
+    CKR(launch_snapshot(s));
     return 0;
 }
 
@@ -460,6 +476,7 @@ static int enqueue_driveout(b200lp_solver* s, const b200lp_opts* o) {
     CK(cudaGetLastError());
     CKR(launch_ratio(s, o->eps_pivot, true, nullptr, 0));
     CKR(launch_update(s, o->update_variant));
+    CKR(launch_snapshot(s));
     return 0;
 }
 
@@ -484,6 +501,8 @@ static int get_graph(b200lp_solver* s, const b200lp_opts* o, int64_t obj_row, in
     k.eps_cost = o->eps_cost;
     k.eps_pivot = o->eps_pivot;
     k.hist_cap = s->hist_cap;
+    k.snaps = s->snaps;
+    k.snap_cap = s->snap_cap;
     if (s->graph && k == s->graph_key) return 0;
     if (s->graph) {
         cudaGraphExecDestroy(s->graph);
@@ -515,7 +534,7 @@ static int run_loop(b200lp_solver* s, const b200lp_opts* o, int64_t obj_row, int
     if (mode == 1) iters = std::min(iters, 8);
     const bool use_graph = o->use_graph && mode == 0;
     if (use_graph) CKR(get_graph(s, o, obj_row, iters));
-    const int per_iter = 3;
+    const int per_iter = s->snaps ? 4 : 3;
     int slot = 0;
     bool first = true;
     for (;;) {
@@ -679,10 +698,9 @@ B200LP_API int b200lp_solve(b200lp_solver* s, const b200lp_opts* o, b200lp_resul
 // ------------------------------------------------------------------------------------------------------
 // one LP from arrays (the linprog seam)
 // ------------------------------------------------------------------------------------------------------
-B200LP_API int b200lp_solve_dense(b200lp_solver* s, const b200lp_problem* p, const b200lp_opts* o, b200lp_result* r) {
+B200LP_API int b200lp_build_dense(b200lp_solver* s, const b200lp_problem* p) {
     if (!s) return fail(B200LP_E_INVALID, "solver is NULL");
-    if (!p || !r) return fail(B200LP_E_INVALID, "problem/result is NULL");
-    CKR(check_opts(o));
+    if (!p) return fail(B200LP_E_INVALID, "problem is NULL");
     const int64_t m = p->m, n = p->n;
     if (m < 0 || n < 0) return fail(B200LP_E_INVALID, "negative dimensions");
     if (n > 0 && !p->c) return fail(B200LP_E_INVALID, "c is NULL");
@@ -760,9 +778,26 @@ B200LP_API int b200lp_solve_dense(b200lp_solver* s, const b200lp_problem* p, con
     }
     // the host vectors above must outlive the async copies
     CK(cudaStreamSynchronize(s->stream));
+    (void)l0;
+    return 0;
+}
+
+B200LP_API int b200lp_solve_dense(b200lp_solver* s, const b200lp_problem* p, const b200lp_opts* o, b200lp_result* r) {
+    if (!s) return fail(B200LP_E_INVALID, "solver is NULL");
+    if (!p || !r) return fail(B200LP_E_INVALID, "problem/result is NULL");
+    CKR(check_opts(o));
+    const int64_t l0 = s->launches;
+    CKR(b200lp_build_dense(s, p));
     const int64_t built = s->launches - l0;
     CKR(b200lp_solve(s, o, r));
     r->kernel_launches += built;
+    return 0;
+}
+
+B200LP_API int b200lp_set_snapshots(b200lp_solver* s, double* snaps_dev, int64_t cap) {
+    if (!s) return fail(B200LP_E_INVALID, "solver is NULL");
+    s->snaps = (snaps_dev && cap > 0) ? snaps_dev : nullptr;
+    s->snap_cap = s->snaps ? cap : 0;
     return 0;
 }
 
@@ -850,6 +885,51 @@ B200LP_API int b200lp_time_update(b200lp_solver* s, int64_t row, int64_t col, in
     if (ms_per_launch) *ms_per_launch = (double)ms / reps;
     CKR(launch_flush(s));
     CK(cudaStreamSynchronize(s->stream));
+    return 0;
+}
+
+// `iters` iterations of the loop with plain launches and CUDA events around every kernel: the live per-kernel
+// durations that bench.py reports in "roofline" (kernels in their real order, caches in their real state).
+B200LP_API int b200lp_profile_loop(b200lp_solver* s, const b200lp_opts* o, int64_t obj_row, int32_t iters,
+                                   double* ms_price, double* ms_ratio, double* ms_update, int64_t* pivots_done) {
+    if (!s || !s->T) return fail(B200LP_E_STATE, "no tableau bound");
+    CKR(check_opts(o));
+    if (iters < 1 || iters > 4096) return fail(B200LP_E_INVALID, "iters out of range");
+    if (obj_row < s->m || obj_row >= s->R) return fail(B200LP_E_INVALID, "obj_row %lld is not an objective row", (long long)obj_row);
+    CKR(set_device(s));
+    CKR(launch_flush(s));
+    CKR(ensure_hist(s, 16));
+    CKR(launch_reset(s, iters, false));
+    std::vector<cudaEvent_t> ev((size_t)iters * 4);
+    for (auto& e : ev) CK(cudaEventCreate(&e));
+    for (int i = 0; i < iters; ++i) {
+        CK(cudaEventRecord(ev[(size_t)i * 4 + 0], s->stream));
+        CKR(launch_price(s, obj_row, o->rule, o->eps_cost, false));
+        CK(cudaEventRecord(ev[(size_t)i * 4 + 1], s->stream));
+        CKR(launch_ratio(s, o->eps_pivot, false, nullptr, 0));
+        CK(cudaEventRecord(ev[(size_t)i * 4 + 2], s->stream));
+        CKR(launch_update(s, o->update_variant));
+        CK(cudaEventRecord(ev[(size_t)i * 4 + 3], s->stream));
+    }
+    CKR(launch_flush(s));
+    DevState st;
+    CKR(read_state(s, &st));
+    double tp = 0, tr = 0, tu = 0;
+    const int64_t done = std::max<int64_t>(1, std::min<int64_t>(st.n_pivots, iters));
+    for (int64_t i = 0; i < done; ++i) {
+        float a = 0, b = 0, c = 0;
+        CK(cudaEventElapsedTime(&a, ev[(size_t)i * 4 + 0], ev[(size_t)i * 4 + 1]));
+        CK(cudaEventElapsedTime(&b, ev[(size_t)i * 4 + 1], ev[(size_t)i * 4 + 2]));
+        CK(cudaEventElapsedTime(&c, ev[(size_t)i * 4 + 2], ev[(size_t)i * 4 + 3]));
+        tp += a;
+        tr += b;
+        tu += c;
+    }
+    for (auto& e : ev) cudaEventDestroy(e);
+    if (ms_price) *ms_price = tp / done;
+    if (ms_ratio) *ms_ratio = tr / done;
+    if (ms_update) *ms_update = tu / done;
+    if (pivots_done) *pivots_done = st.n_pivots;
     return 0;
 }
 

@@ -43,6 +43,10 @@ __global__ void __launch_bounds__(256)
 k_generate(double* __restrict__ T, int64_t m, int64_t R, int64_t C, int64_t ld, uint64_t seed, int64_t n_total,
            int64_t lab0, int32_t* __restrict__ rowlab, int32_t* __restrict__ collab) {
     const int64_t j = 2 * ((int64_t)blockIdx.x * blockDim.x + threadIdx.x);
+    if (blockIdx.x == 0) {
+        for (int64_t i = blockIdx.y * blockDim.x + threadIdx.x; i < R; i += (int64_t)gridDim.y * blockDim.x)
+            rowlab[i] = i < m ? (int32_t)(n_total + i) : -1;
+    }
     if (j >= ld) return;
     const int64_t labx = (j < C - 1) ? lab0 + j : -1;
     const int64_t laby = (j + 1 < C - 1) ? lab0 + j + 1 : -1;
@@ -55,10 +59,6 @@ k_generate(double* __restrict__ T, int64_t m, int64_t R, int64_t C, int64_t ld, 
     if (blockIdx.y == 0) {
         if (j < C) collab[j] = (int32_t)labx;
         if (j + 1 < C) collab[j + 1] = (int32_t)laby;
-    }
-    if (blockIdx.x == 0) {
-        for (int64_t i = blockIdx.y * blockDim.x + threadIdx.x; i < R; i += (int64_t)gridDim.y * blockDim.x)
-            rowlab[i] = i < m ? (int32_t)(n_total + i) : -1;
     }
 }
 

@@ -314,6 +314,26 @@ k_driveout_pick(const double* __restrict__ T, int64_t m, int64_t C, int64_t ld, 
     }
 }
 
+// Optional (small LPs that feed the reference's "pivotSteps", solver_controller.py:332-362): keep a dense copy of
+// the tableau after every pivot.  Row r is still unscaled at this point, so the scaling is applied on the fly.
+__global__ void __launch_bounds__(256)
+k_snapshot(const double* __restrict__ T, int64_t R, int64_t C, int64_t ld, const DevState* __restrict__ st,
+           double* __restrict__ snaps, int64_t cap) {
+    if (st->done || !st->have_pivot) return;
+    const long long slot = st->n_pivots - 1;
+    if (slot < 0 || slot >= cap) return;
+    const int r = st->r, s = st->s;
+    const double p = st->p, inv_p = st->inv_p;
+    double* out = snaps + slot * R * C;
+    const int64_t total = R * C;
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t i = e / C, j = e - i * C;
+        double v = T[i * ld + j];
+        if (i == r) v = (j == s) ? inv_p : v / p;
+        out[e] = v;
+    }
+}
+
 __global__ void k_set_pivot(DevState* st, int32_t r, int32_t s, const int32_t* collab) {
     st->done = 0;
     st->have_pivot = 1;

@@ -33,7 +33,8 @@ EXPORTS = [
     "b200lp_generate", "b200lp_set_labels", "b200lp_get_labels", "b200lp_read_tableau", "b200lp_read_solution",
     "b200lp_run", "b200lp_solve", "b200lp_select_entering", "b200lp_ratio_test", "b200lp_pivot",
     "b200lp_shard_candidate", "b200lp_shard_pivot", "b200lp_shard_state", "b200lp_shard_reset",
-    "b200lp_read_history", "b200lp_solve_batched", "b200lp_time_update",
+    "b200lp_read_history", "b200lp_solve_batched", "b200lp_time_update", "b200lp_build_dense",
+    "b200lp_set_snapshots", "b200lp_profile_loop",
 ]
 
 _f64p = C.POINTER(C.c_double)
@@ -105,6 +106,8 @@ def lib():
                 L.b200lp_set_stream.argtypes = [C.c_void_p, C.c_void_p]
                 L.b200lp_synchronize.argtypes = [C.c_void_p]
                 L.b200lp_solve_dense.argtypes = [C.c_void_p, C.POINTER(Problem), C.POINTER(Opts), C.POINTER(Result)]
+                L.b200lp_build_dense.argtypes = [C.c_void_p, C.POINTER(Problem)]
+                L.b200lp_set_snapshots.argtypes = [C.c_void_p, C.c_void_p, C.c_int64]
                 L.b200lp_attach.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_int64,
                                             C.c_int64, C.c_int32]
                 L.b200lp_dims.argtypes = [C.c_void_p] + [C.POINTER(C.c_int64)] * 4
@@ -131,6 +134,8 @@ def lib():
                                                    C.POINTER(C.c_double)]
                 L.b200lp_time_update.argtypes = [C.c_void_p, C.c_int64, C.c_int64, C.c_int32, C.c_int32,
                                                  C.POINTER(C.c_double)]
+                L.b200lp_profile_loop.argtypes = [C.c_void_p, C.POINTER(Opts), C.c_int64, C.c_int32] + \
+                    [C.POINTER(C.c_double)] * 3 + [C.POINTER(C.c_int64)]
                 _lib = L
     return _lib
 
@@ -232,6 +237,22 @@ class Solver:
         check(lib().b200lp_solve_dense(self._h, C.byref(p), C.byref(opts), C.byref(res)))
         return self._result_dict(res, keep, n)
 
+    def build_dense(self, A, b, c, ops):
+        """First half of solve_dense: build the initial tableau on the device (host ndarrays in)."""
+        A = np.ascontiguousarray(A, dtype=np.float64)
+        b = np.ascontiguousarray(b, dtype=np.float64)
+        c = np.ascontiguousarray(c, dtype=np.float64)
+        ops = np.ascontiguousarray(ops, dtype=np.int8)
+        m, n = len(b), len(c)
+        p = Problem(m, n, n, _ptr(A), _ptr(b), _ptr(c), _ptr(ops), 0, 0)
+        check(lib().b200lp_build_dense(self._h, C.byref(p)))
+        mm, n_obj, Ccols, ld = self.dims()
+        self._dims = (mm, n_obj, Ccols, ld, n)
+
+    def set_snapshots(self, ptr: int | None, cap: int = 0, keep=None):
+        check(lib().b200lp_set_snapshots(self._h, C.c_void_p(ptr or 0), cap))
+        self._keep_snaps = keep
+
     # ---- device-resident tableau ----------------------------------------------------------------------
     def attach(self, T_ptr: int, m: int, n_obj: int, Ccols: int, ld: int, n_struct: int, art_base: int, keep=None):
         check(lib().b200lp_attach(self._h, C.c_void_p(T_ptr), m, n_obj, Ccols, ld, n_struct, art_base))
@@ -307,6 +328,14 @@ class Solver:
         ms = C.c_double()
         check(lib().b200lp_time_update(self._h, row, col, update_variant, reps, C.byref(ms)))
         return float(ms.value)
+
+    def profile_loop(self, opts: Opts, iters: int = 16, obj_row: int | None = None):
+        """Average ms of the price / ratio / update kernels over `iters` real loop iterations (CUDA events)."""
+        m, _, _, _ = self.dims()
+        a, b, c, n = C.c_double(), C.c_double(), C.c_double(), C.c_int64()
+        check(lib().b200lp_profile_loop(self._h, C.byref(opts), m if obj_row is None else obj_row, iters,
+                                        C.byref(a), C.byref(b), C.byref(c), C.byref(n)))
+        return {"price_ms": a.value, "ratio_ms": b.value, "update_ms": c.value, "pivots": int(n.value)}
 
     # ---- column shards ----------------------------------------------------------------------------------
     def shard_reset(self, max_pivots: int):

@@ -1,0 +1,181 @@
+"""GPU tests of the reference-facing host API: the linprog seam, the SolverController mirror and its report,
+the pivotSteps producer, the plugin patching, and the column-shard engine (world = 1) against the oracle."""
+import sys
+import types
+
+import numpy as np
+import pytest
+
+from simplex_solver_b200 import native, workloads as W
+from simplex_solver_b200.linprog import linprog
+from simplex_solver_b200.sharded import CudaShardEngine, ShardedTableau
+from simplex_solver_b200.solver_controller import BulkSolverController, SolverController
+from tests.helpers import assert_bit_equal
+
+pytestmark = pytest.mark.gpu
+REL = 1e-9
+
+
+def test_linprog_seam_on_reference_fixtures(golden):
+    for name, g in golden["kat"].items():
+        ctl = SolverController(g["problem"])
+        c, A_ub, b_ub, A_eq, b_eq, bounds = ctl._prepare_model_for_scipy(ctl.objective_data, ctl.constraints_data,
+                                                                        ctl.variables)
+        r = linprog(c, A_ub=A_ub, b_ub=b_ub, A_eq=A_eq, b_eq=b_eq, bounds=bounds, method="highs-ds",
+                    options={"presolve": True, "time_limit": 10})
+        assert r.status == g["scipy_status"], name
+        assert r.success == (g["scipy_status"] == 0)
+        assert isinstance(r.message, str) and r.message
+        if r.success:
+            z = -r.fun if ctl.objective_data["type"] == "maximize" else r.fun
+            assert abs(z - g["z"]) <= REL * max(1.0, abs(g["z"])), name
+            assert len(r.x) == len(ctl.variables)
+        else:
+            assert r.x is None and r.fun is None
+
+
+def test_solver_controller_report_wyndor(golden, tmp_path):
+    """BASELINE config 1 through the mirror class: same report keys / strings as the reference (:417-422)."""
+    wrapper = golden["kat"]["K1_wyndor"]["problem"]
+    rep = SolverController(wrapper, output_dir=str(tmp_path)).run()
+    assert set(rep) == {"problema_definicion", "solucion_encontrada", "visualizacion_gilp_html", "tablas_intermedias"}
+    sol = rep["solucion_encontrada"]
+    assert sol["status"] == "Solucion Factible"
+    assert abs(sol["valor_optimo_z"] - 36.0) < 1e-9
+    assert abs(sol["valores_variables"]["x1"] - 2.0) < 1e-9 and abs(sol["valores_variables"]["x2"] - 6.0) < 1e-9
+    assert f"{sol['valor_optimo_z']:.4f}" == "36.0000"
+    tabs = rep["tablas_intermedias"]
+    assert tabs[0]["title"] == "Iteración 0 (Tabla Inicial)" and tabs[0]["pivot"] is None
+    assert len(tabs) == 3 and tabs[1]["pivot"] is not None                      # Dantzig: 2 pivots
+    assert tabs[0]["table"][0][0] == "Base" and tabs[0]["table"][1][0] == "F0"
+    # final tableau: objective row's last cell is z*, basic columns are unit vectors
+    last = tabs[-1]["table"]
+    assert last[4][-1] == 36.0
+    assert "<table" in rep["visualizacion_gilp_html"] and "Iteración 2" in rep["visualizacion_gilp_html"]
+    assert (tmp_path / "solucion_1.json").exists()
+    import json
+    json.load(open(tmp_path / "solucion_1.json"))
+
+
+def test_solver_controller_statuses(golden):
+    rep = SolverController(golden["kat"]["K6_infeasible"]["problem"]).run()
+    assert rep["solucion_encontrada"]["status"] == "Sin Solucion Factible"
+    assert rep["solucion_encontrada"]["valores_variables"] is None and rep["tablas_intermedias"] == []
+    rep = SolverController(golden["kat"]["K7_unbounded"]["problem"]).run()
+    assert rep["solucion_encontrada"]["status"] == "Error"
+
+
+def test_pivot_steps_full_tableau_is_consistent(golden):
+    """Every displayed tableau satisfies the invariant of a simplex tableau: basic columns are unit vectors and
+    B^-1-consistency: T_k = E_k T_{k-1} for the elementary pivot matrix (checked through the RHS/objective)."""
+    from simplex_solver_b200.simple_simplex import add_constraint, add_objective, create_tableau, optimize_json_format
+    for name in ("K1_wyndor", "K3_min_ge", "K5_eq", "K9_three_var"):
+        A, b, c, ops, mx, _ = W.problem_dict_to_arrays(golden["kat"][name]["problem"])
+        t = create_tableau(len(c), len(b))
+        for i in range(len(b)):
+            add_constraint(t, ",".join(str(v) for v in A[i]) + f",{'LGE'[ops[i]]},{b[i]}")
+        add_objective(t, ",".join(str(v) for v in c) + f",{1 if mx else 0}")
+        js = optimize_json_format(t, maximize=mx)
+        steps = js["pivotSteps"]
+        assert steps[0]["step"] == 0 and steps[0]["pivotRowIndex"] is None
+        m = len(b)
+        for k, st in enumerate(steps):
+            T = np.array(st["tableau"])
+            assert st["step"] == k
+            for i, lab in enumerate(st["basis"]):
+                colnames = js["columns"]
+                assert len(colnames) == T.shape[1]
+            if k > 0:
+                r, cidx = st["pivotRowIndex"], st["pivotColIndex"]
+                prev = np.array(steps[k - 1]["tableau"])
+                p = prev[r, cidx]
+                exp = prev - np.outer(prev[:, cidx], prev[r] / p)
+                exp[r] = prev[r] / p
+                np.testing.assert_allclose(T, exp, rtol=1e-12, atol=1e-12, err_msg=f"{name} step {k}")
+                assert abs(T[r, cidx] - 1.0) < 1e-12
+        z = js["optimalValue"]
+        assert abs(z - golden["kat"][name]["z"]) <= REL * max(1.0, abs(z))
+        final = np.array(steps[-1]["tableau"])
+        assert abs(abs(final[m, -1]) - abs(z)) <= 1e-9 * max(1.0, abs(z))
+
+
+def test_plugin_patches_the_reference_seam(golden):
+    """patch the five names in a stand-in for app.controllers.solver_controller."""
+    from simplex_solver_b200 import plugin
+    fake = types.ModuleType("app.controllers.solver_controller")
+    fake.linprog = lambda *a, **k: (_ for _ in ()).throw(RuntimeError("cpu path"))
+    plugin.install(fake)
+    try:
+        r = fake.linprog([-3.0, -5.0], A_ub=[[1, 0], [0, 2], [3, 2]], b_ub=[4, 12, 18], bounds=[(0, None)] * 2,
+                         method="highs-ds", options={"presolve": True, "time_limit": 10})
+        assert r.success and abs(r.fun + 36.0) < 1e-9
+        tab = fake.create_tableau(number_of_variables=2, number_of_constraints=3)
+        fake.add_constraint(tab, "1.0,0.0,L,4.0")
+        fake.add_constraint(tab, "0.0,2.0,L,12.0")
+        fake.add_constraint(tab, "3.0,2.0,L,18.0")
+        fake.add_objective(tab, "3.0,5.0,1")
+        js = fake.optimize_json_format(tab, maximize=True)
+        assert "pivotSteps" in js and len(js["pivotSteps"]) == 3
+    finally:
+        plugin.uninstall(fake)
+    with pytest.raises(RuntimeError):
+        fake.linprog([1.0])
+
+
+def test_bulk_controller_config2_small(golden):
+    A, b, c, ops, mx = W.dense_feasible_lp(128, seed=0)
+    out = BulkSolverController(A, b, c, ops, mx).run()
+    assert out["status"] == "Solucion Factible"
+    zg = golden["dense"]["128"]["z"]
+    assert abs(out["valor_optimo_z"] - zg) <= REL * abs(zg)
+
+
+@pytest.mark.parametrize("rule", [native.RULE_BLAND, native.RULE_DANTZIG])
+def test_cuda_shard_engine_world1_and_emulated_world2(oracle, rule):
+    """The shard kernels (candidate / winner / ratio on an external column / update with a remote column) against
+    the oracle.  Two shards are emulated in ONE process on one GPU (two solvers, gather by copy), which exercises
+    the remote-column path without needing two GPUs."""
+    import torch
+    m, n_total, seed, budget = 96, 160, 4, 80
+    one = oracle.OracleTableau.generate(seed, m, n_total)
+    ref = one.solve(oracle.make_opts(rule=rule, max_pivots=budget), hist_cap=budget)
+    opts = native.make_opts(rule=rule, max_pivots=budget)
+
+    eng = CudaShardEngine(m, n_total, 0, n_total, seed)
+    status, n = ShardedTableau(eng, 1, 0).run(opts, budget, check_every=16)
+    assert status == ref["status"] and n == ref["n_pivots"]
+    h = eng.history(budget)
+    np.testing.assert_array_equal(h["piv_row"], ref["piv_row"])
+    np.testing.assert_array_equal(h["enter_lab"], ref["enter_lab"])
+    assert_bit_equal(eng.tableau(), one.T, "world-1 shard tableau")
+
+    world = 2
+    engs = []
+    for r in range(world):
+        lo, hi = ShardedTableau.columns_of(n_total, world, r)
+        engs.append(CudaShardEngine(m, n_total, lo, hi - lo, seed))
+    gathered = engs[0].new_buffer(world)
+    for e in engs:
+        e.reset(budget)
+    stride = m + 1 + 2
+    for _ in range(budget + 2):
+        for r, e in enumerate(engs):
+            gathered[r * stride:(r + 1) * stride].copy_(e.candidate(opts))
+        torch.cuda.synchronize()
+        for r, e in enumerate(engs):
+            e.pivot(opts, gathered, world, r)
+        torch.cuda.synchronize()
+    for r, e in enumerate(engs):
+        done, status, n = e.state()
+        assert done and status == ref["status"] and n == ref["n_pivots"]
+        h = e.history(budget)
+        np.testing.assert_array_equal(h["piv_row"], ref["piv_row"])
+        np.testing.assert_array_equal(h["enter_lab"], ref["enter_lab"])
+        np.testing.assert_array_equal(h["leave_lab"], ref["leave_lab"])
+        T = e.tableau()
+        rl, cl = e.labels()
+        np.testing.assert_array_equal(rl, one.rowlab)
+        pos = {int(lab): j for j, lab in enumerate(one.collab[:-1])}
+        for j, lab in enumerate(cl[:-1]):
+            assert_bit_equal(T[:, j], one.T[:, pos[int(lab)]], f"shard {r} column of variable {lab}")
+        assert_bit_equal(T[:, -1], one.T[:, -1], f"shard {r} rhs replica")

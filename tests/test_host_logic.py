@@ -1,0 +1,181 @@
+"""Host-side mirror of the reference interface: argument translation, report format, sharding arithmetic.
+No GPU needed (the compute calls are not made here)."""
+import numpy as np
+import pytest
+
+from simplex_solver_b200 import native, workloads as W
+from simplex_solver_b200.batched import shard_range
+from simplex_solver_b200.linprog import OptimizeResult, drop_rows_implied_by_equalities, rows_from_linprog_args
+from simplex_solver_b200.sharded import ShardedTableau
+from simplex_solver_b200.simple_simplex import add_constraint, add_objective, create_tableau, expand_full
+from simplex_solver_b200.solver_controller import SolverController, save_solution, status_text
+
+# the reference's own fixtures (tests/test_solver_controller.py:16-40)
+OBJ_MIN = {"type": "minimize", "coefficients": {"x1": 50.0, "x2": 80.0}}
+CONS_MIN = [
+    {"coefficients": {"x1": 4.0, "x2": 1.0}, "operator": ">=", "rhs": 4.0},
+    {"coefficients": {"x1": 1.0, "x2": 6.0}, "operator": ">=", "rhs": 6.0},
+    {"coefficients": {"x1": 4.0, "x2": 6.0}, "operator": ">=", "rhs": 12.0},
+]
+OBJ_MAX = {"type": "maximize", "coefficients": {"x1": 15.0, "x2": 18.0}}
+CONS_MAX = [
+    {"coefficients": {"x1": 4.0, "x2": 2.0}, "operator": "<=", "rhs": 2000.0},
+    {"coefficients": {"x1": 2.0, "x2": 6.0}, "operator": "<=", "rhs": 2400.0},
+    {"coefficients": {"x1": 20.0, "x2": 28.0}, "operator": "<=", "rhs": 14000.0},
+]
+
+
+def _ctl(obj, cons):
+    return SolverController({"problema_definicion": {"funcion_objetivo": obj, "restricciones": cons}})
+
+
+def test_prepare_model_maximize_matches_reference_expectation():
+    # expectations of /root/reference/tests/test_solver_controller.py:66-76
+    ctl = _ctl(OBJ_MAX, CONS_MAX)
+    c, A_ub, b_ub, A_eq, b_eq, bounds = ctl._prepare_model_for_scipy(OBJ_MAX, CONS_MAX, ctl.variables)
+    np.testing.assert_array_equal(c, np.array([-15.0, -18.0]))
+    np.testing.assert_array_equal(A_ub, np.array([[4.0, 2.0], [2.0, 6.0], [20.0, 28.0]]))
+    np.testing.assert_array_equal(b_ub, np.array([2000.0, 2400.0, 14000.0]))
+    assert A_eq is None and b_eq is None
+    assert bounds == [(0, None), (0, None)]
+
+
+def test_prepare_model_minimize_matches_reference_expectation():
+    # expectations of /root/reference/tests/test_solver_controller.py:95-103
+    ctl = _ctl(OBJ_MIN, CONS_MIN)
+    c, A_ub, b_ub, A_eq, b_eq, _ = ctl._prepare_model_for_scipy(OBJ_MIN, CONS_MIN, ctl.variables)
+    np.testing.assert_array_equal(c, np.array([50.0, 80.0]))
+    np.testing.assert_array_equal(A_ub, np.array([[-4.0, -1.0], [-1.0, -6.0], [-4.0, -6.0]]))
+    np.testing.assert_array_equal(b_ub, np.array([-4.0, -6.0, -12.0]))
+
+
+def test_prepare_model_equality_arrives_three_times_and_is_deduplicated():
+    obj = {"type": "maximize", "coefficients": {"x1": 1.0, "x2": 1.0}}
+    cons = [{"coefficients": {"x1": 1.0, "x2": 1.0}, "operator": "=", "rhs": 10.0},
+            {"coefficients": {"x1": 2.0, "x2": 1.0}, "operator": "<=", "rhs": 15.0}]
+    ctl = _ctl(obj, cons)
+    c, A_ub, b_ub, A_eq, b_eq, _ = ctl._prepare_model_for_scipy(obj, cons, ctl.variables)
+    assert A_ub.shape == (3, 2) and A_eq.shape == (1, 2)       # solver_controller.py:154-161
+    cc, A, b, ops = rows_from_linprog_args(c, A_ub, b_ub, A_eq, b_eq)
+    assert A.shape == (2, 2)
+    np.testing.assert_array_equal(ops, [native.OP_LE, native.OP_EQ])
+    np.testing.assert_array_equal(A, [[2.0, 1.0], [1.0, 1.0]])
+    np.testing.assert_array_equal(b, [15.0, 10.0])
+
+
+def test_dedup_keeps_unrelated_rows_and_handles_signed_zero():
+    A_eq = np.array([[1.0, 0.0]])
+    b_eq = np.array([0.0])
+    A_ub = np.array([[1.0, 0.0], [-1.0, -0.0], [1.0, 1.0]])
+    b_ub = np.array([0.0, -0.0, 3.0])
+    A2, b2 = drop_rows_implied_by_equalities(A_ub, b_ub, A_eq, b_eq)
+    np.testing.assert_array_equal(A2, [[1.0, 1.0]])
+    np.testing.assert_array_equal(b2, [3.0])
+
+
+def test_missing_coefficients_read_as_zero_and_variable_order_is_lexicographic():
+    obj = {"type": "minimize", "coefficients": {"x1": 1.0, "x10": 3.0, "x2": 2.0}}
+    cons = [{"coefficients": {"x2": 5.0}, "operator": "<=", "rhs": 1.0}]
+    ctl = _ctl(obj, cons)
+    assert ctl.variables == ["x1", "x10", "x2"]                # solver_controller.py:46
+    c, A_ub, *_ = ctl._prepare_model_for_scipy(obj, cons, ctl.variables)
+    np.testing.assert_array_equal(c, [1.0, 3.0, 2.0])
+    np.testing.assert_array_equal(A_ub, [[0.0, 0.0, 5.0]])
+
+
+def test_empty_wrapper_returns_none_like_the_reference():
+    # /root/reference/tests/test_solver_controller.py:225-245
+    assert SolverController({}).run() is None
+    assert SolverController({"problema_definicion": {}}).run() is None
+
+
+def test_status_strings():
+    assert status_text(OptimizeResult(success=True, status=0)) == "Solucion Factible"
+    assert status_text(OptimizeResult(success=False, status=2)) == "Sin Solucion Factible"
+    for st in (1, 3, 4):
+        assert status_text(OptimizeResult(success=False, status=st)) == "Error"   # solver_controller.py:404
+
+
+def test_extract_tableaus_format():
+    js = {"pivotSteps": [
+        {"step": 0, "pivotRowIndex": None, "pivotColIndex": None, "tableau": [[1.0, 2.0], [3.0, 4.123456]]},
+        {"step": 1, "pivotRowIndex": 1, "pivotColIndex": 0, "tableau": [[1.0, 2.0], [1.0, 0.33333333]]},
+    ]}
+    out = SolverController._extract_tableaus_from_simple_simplex(js)
+    assert out[0]["title"] == "Iteración 0 (Tabla Inicial)" and out[0]["pivot"] is None
+    assert out[1]["title"] == "Iteración 1 (Pivote: Fila 1, Col 0)" and out[1]["pivot"] == (1, 0)
+    assert out[0]["table"][0] == ["Base", "C0", "C1"]
+    assert out[0]["table"][2] == ["F1", 3.0, 4.1235]            # rounded to 4 dp (solver_controller.py:354)
+    assert SolverController._extract_tableaus_from_simple_simplex({}) == []
+    html = SolverController._tableau_to_html(out[1]["table"], 1, 0)
+    assert html.count("<tr>") == 3 and "0.3333" in html and "background-color:#fff0f0" in html
+
+
+def test_simple_simplex_string_api():
+    t = create_tableau(number_of_variables=2, number_of_constraints=2)
+    add_constraint(t, "1.0,0.0,L,4.0")
+    add_constraint(t, "3.0,2.0,G,18.0")
+    add_objective(t, "3.0,5.0,1")
+    assert t["rows"] == [([1.0, 0.0], native.OP_LE, 4.0), ([3.0, 2.0], native.OP_GE, 18.0)]
+    assert t["objective"] == [3.0, 5.0] and t["maximize_flag"] is True
+    with pytest.raises(ValueError):
+        add_constraint(t, "1.0,L,4.0")
+    with pytest.raises(ValueError):
+        add_constraint(create_tableau(2, 1), "1.0,2.0,X,4.0")
+
+
+def test_expand_full_scatters_unit_columns():
+    # condensed 2 constraint rows + objective; variables: x0, x1 structural, s2, s3 slacks
+    Tc = np.array([[2.0, 5.0, 10.0], [3.0, 7.0, 20.0], [-1.0, -4.0, 0.0]])
+    rowlab = np.array([2, 0, -1])        # row 0: slack 2 basic, row 1: x0 basic
+    collab = np.array([3, 1, -1])        # columns: slack 3, x1, RHS
+    full = expand_full(Tc, rowlab, collab, [0, 1, 2, 3], 2)
+    np.testing.assert_array_equal(full, [[0, 5, 1, 2, 10], [1, 7, 0, 3, 20], [0, -4, 0, -1, 0]])
+
+
+def test_save_solution_is_sequential_and_serialises_numpy(tmp_path):
+    rep = {"solucion_encontrada": {"valor_optimo_z": np.float64(36.0), "valores_variables": {"x1": np.float64(2.0)}}}
+    p1 = save_solution(rep, str(tmp_path))
+    p2 = save_solution(rep, str(tmp_path))
+    assert p1.endswith("solucion_1.json") and p2.endswith("solucion_2.json")
+    import json
+    assert json.load(open(p1))["solucion_encontrada"]["valor_optimo_z"] == 36.0
+
+
+def test_shard_ranges_partition_everything():
+    for total in (0, 1, 7, 100000, 131070):
+        for world in (1, 2, 3, 4, 8):
+            for align in (1, 2, 1000):
+                parts = [shard_range(total, world, r, align) for r in range(world)]
+                assert parts[0][0] == 0 and parts[-1][1] == total
+                for (a, b), (c, d) in zip(parts, parts[1:]):
+                    assert b == c and a <= b
+                for lo, hi in parts[:-1]:
+                    assert lo % align == 0 and hi % align == 0 or hi == total
+    assert ShardedTableau.columns_of(131064, 8, 3) == (49148, 65532)
+    assert ShardedTableau.columns_of(10, 2, 1) == (4, 10)
+
+
+def test_workload_generators_shapes_and_special_cases():
+    A, b, c, ops = W.batched_small_lps(0, 300)
+    assert A.shape == (300, 20, 30) and b.shape == (300, 20) and c.shape == (300, 30) and ops.dtype == np.int8
+    assert ops[0, 0] == W.LE and ops[0, 1] == W.GE and b[0, 0] == 5.0 and b[0, 1] == 10.0   # infeasible pattern
+    assert (ops[1] == W.GE).all() and (A[1] >= 0).all() and (c[1] < 0).all()                 # unbounded pattern
+    A2, b2, c2, ops2 = W.batched_small_lps(1000, 10)
+    A3, _, _, _ = W.batched_small_lps(0, 1010)
+    np.testing.assert_array_equal(A2, A3[1000:])          # shards regenerate exactly their slice
+    wrapper = W.lp_to_problem_dict(A[2], b[2], c[2], ops[2], False)
+    Ar, br, cr, opr, mx, names = W.problem_dict_to_arrays(wrapper)
+    np.testing.assert_array_equal(Ar, A[2])
+    np.testing.assert_array_equal(opr, ops[2])
+    assert names == sorted(names) and not mx
+
+
+def test_linprog_rejects_unsupported_bounds():
+    from simplex_solver_b200.linprog import _check_bounds
+    _check_bounds([(0, None)] * 3, 3)
+    _check_bounds((0, None), 3)
+    with pytest.raises(NotImplementedError):
+        _check_bounds([(1, None)], 1)
+    with pytest.raises(NotImplementedError):
+        _check_bounds([(0, 5.0)], 1)
