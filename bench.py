@@ -57,7 +57,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(self.gpu)],
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "50", "-i", str(self.gpu)],
                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -66,7 +66,16 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.lines.append(line.strip())
+            self.lines.append((time.monotonic(), line.strip()))
+
+    def wait_first(self, timeout=5.0):
+        t0 = time.monotonic()
+        while not self.lines and time.monotonic() - t0 < timeout:
+            time.sleep(0.02)
+
+    def mark(self):
+        """Only samples that arrive after this call are reported (call it when the timed region starts)."""
+        self.t_mark = time.monotonic()
 
     def stop(self):
         if not self.proc:
@@ -77,7 +86,10 @@ class ClockSampler:
         except Exception:
             self.proc.kill()
         sm, mx, reasons = [], [], set()
-        for ln in self.lines:
+        t_mark = getattr(self, "t_mark", 0.0)
+        for ts, ln in self.lines:
+            if ts < t_mark:
+                continue
             f = [x.strip() for x in ln.split(",")]
             if len(f) < 8:
                 continue
@@ -175,9 +187,16 @@ def workload_config(args):
 # ----------------------------------------------------------------------------------------------------------
 def bench_single_gpu(args):
     import torch
+    torch.cuda.set_device(0)
+    # one explicit non-default stream carries the solver's kernels, torch's copies and the timing events
+    with torch.cuda.stream(torch.cuda.Stream()):
+        _bench_single_gpu(args)
+
+
+def _bench_single_gpu(args):
+    import torch
     from simplex_solver_b200 import native
 
-    torch.cuda.set_device(0)
     R = args.rows
     m = n = R - 1
     C = ld = R
@@ -193,11 +212,13 @@ def bench_single_gpu(args):
     bytes_per_pivot = 16.0 * R * C
 
     launches = 0
+    sampler = ClockSampler(0)
+    sampler.start()
+    sampler.wait_first()
     for _ in range(args.warmup):
         s.run(opts)
     torch.cuda.synchronize()
-    sampler = ClockSampler(0)
-    sampler.start()
+    sampler.mark()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record()
     pivots = 0
@@ -374,6 +395,16 @@ def bench_sharded(args):
     world = int(os.environ.get("WORLD_SIZE", "1"))
     torch.cuda.set_device(local)
     dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
+    with torch.cuda.stream(torch.cuda.Stream()):
+        _bench_sharded(args, rank, local, world)
+    dist.destroy_process_group()
+
+
+def _bench_sharded(args, rank, local, world):
+    import torch
+    import torch.distributed as dist
+    from simplex_solver_b200 import native
+    from simplex_solver_b200.sharded import CudaShardEngine, ShardedTableau
     R = args.rows
     m = R - 1
     c_loc = args.cols_total // world            # stored columns per shard, RHS replica included
@@ -388,13 +419,15 @@ def bench_sharded(args):
     eng = make_engine()
     drv = ShardedTableau(eng, world, rank)
     torch.cuda.synchronize()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+        sampler.wait_first()
     for _ in range(args.warmup):
         drv.run(opts, args.pivots, check_every=args.pivots)
     torch.cuda.synchronize()
     dist.barrier()
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
+    sampler.mark()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record()
     pivots = 0
@@ -457,7 +490,6 @@ def bench_sharded(args):
             "collective": {"op": "all_gather_into_tensor (NCCL)", "bytes_per_rank_per_pivot": 8 * (R + 2)},
         }
         print(json.dumps(line))
-    dist.destroy_process_group()
 
 
 def main():

@@ -113,8 +113,11 @@ void b200lp_default_opts(b200lp_opts *opts);
 /* ---- workspace -------------------------------------------------------------------------------------- */
 int b200lp_create(b200lp_solver **out, int device);
 int b200lp_destroy(b200lp_solver *s);
-/* run the solver's kernels on a caller stream (cudaStream_t as void*; NULL restores the solver's own) */
+/* run the solver's kernels on a caller stream (cudaStream_t as void*, used as given: 0 is the legacy default
+ * stream, on which the loop uses plain launches because CUDA graphs cannot be captured there);
+ * b200lp_use_own_stream goes back to the solver's own non-blocking stream (the default after create). */
 int b200lp_set_stream(b200lp_solver *s, void *stream);
+int b200lp_use_own_stream(b200lp_solver *s);
 int b200lp_synchronize(b200lp_solver *s);
 
 /* ---- one LP, reference-facing (linprog seam) --------------------------------------------------------- */

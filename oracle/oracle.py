@@ -133,8 +133,11 @@ class OracleTableau:
         return self
 
     def __del__(self):
-        if self._alive:
-            lib().orc_free(C.byref(self.t))
+        if self._alive and _lib is not None and C is not None:
+            try:
+                _lib.orc_free(C.byref(self.t))
+            except Exception:
+                pass
             self._alive = False
 
     # numpy views (no copy)

@@ -132,35 +132,55 @@ __device__ __forceinline__ void store_wait_all() { asm volatile("cp.async.bulk.w
 }  // namespace tma
 
 constexpr int TMA_BOX_C = 256;                   // doubles per tile row (2 KB)
-constexpr int TMA_BOX_R = 16;                    // rows per tile  -> 32 KB tiles
-constexpr int TMA_STAGES = 6;                    // 6 x 32 KB = 192 KB ring
-constexpr int TMA_STORE_LAG = 2;                 // stores allowed to be still reading shared memory
-constexpr int TMA_TILE_DOUBLES = TMA_BOX_C * TMA_BOX_R;
-constexpr int TMA_TILE_BYTES = TMA_TILE_DOUBLES * 8;
+constexpr int TMA_BOX_R = 16;                    // rows per tile -> 32 KB tiles
+constexpr int TMA_STAGES = 4;                    // ring depth (4 x 34 KB); deeper rings measured slower on B200
+constexpr int TMA_STORE_LAG = 1;                 // stores allowed to be still reading shared memory
 constexpr int TMA_CONSUMERS = 256;               // 8 consumer warps
 constexpr int TMA_THREADS = TMA_CONSUMERS + 32;  // + 1 producer warp
-constexpr size_t TMA_SMEM_BYTES = (size_t)TMA_STAGES * TMA_TILE_BYTES + 1024 /*alignment slack*/ + 128 /*barriers*/;
+
+template <int BOX_R, int STAGES>
+struct TmaCfg {
+    static constexpr int TILE_DOUBLES = TMA_BOX_C * BOX_R;
+    static constexpr int TILE_BYTES = TILE_DOUBLES * 8;
+    static constexpr int COL_BYTES = BOX_R * 8;                       // pivot-column slice of the tile's rows
+    static constexpr int COL_PAD = ((COL_BYTES + 127) / 128) * 128;
+    static constexpr int ROW_BYTES = TMA_BOX_C * 8;                   // pivot-row strip (first tile of a work item)
+    static constexpr int STAGE_BYTES = TILE_BYTES + COL_PAD + ROW_BYTES;
+    static constexpr size_t SMEM_BYTES = (size_t)STAGES * STAGE_BYTES + 1024 /*alignment slack*/ + 256 /*barriers*/;
+    static_assert(SMEM_BYTES <= 232448, "ring does not fit the 227 KB of shared memory a CTA can opt in to");
+    // STORE_LAG = stores allowed to be still reading shared memory when the next tile is processed
+};
+
+__device__ __forceinline__ void bulk_load_1d(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     tma::smem_u32(smem_dst)),
+                 "l"(gsrc), "r"(bytes), "r"(tma::smem_u32(bar))
+                 : "memory");
+}
 
 // Work item = (column strip of TMA_BOX_C columns) x (chunk of `chunk_tiles` row tiles); a CTA walks its items
-// with a grid stride, one resident CTA per SM.
-__global__ void __launch_bounds__(TMA_THREADS, 1)
+// with a grid stride, one resident CTA per SM.  Each stage carries the tile, the slice of the pivot column for
+// the tile's rows and -- on the first tile of a work item -- the pivot-row strip (1-D bulk copies on the same
+// mbarrier), so the consumers never wait on a global load: everything they read arrives through the TMA unit.
+template <int BOX_R, int STAGES, int STORE_LAG, int CTAS_PER_SM>
+__global__ void __launch_bounds__(TMA_THREADS, CTAS_PER_SM)
 k_update_tma(const __grid_constant__ CUtensorMap map, const double* __restrict__ T, int64_t R, int64_t C, int64_t ld,
              const double* __restrict__ col, const DevState* __restrict__ st, int strips, int chunk_tiles,
              int64_t n_work) {
+    using Cfg = TmaCfg<BOX_R, STAGES>;
     if (st->done || !st->have_pivot) return;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-    double* tiles = reinterpret_cast<double*>(smem);
-    uint64_t* full = reinterpret_cast<uint64_t*>(smem + (size_t)TMA_STAGES * TMA_TILE_BYTES);
-    uint64_t* empty = full + TMA_STAGES;
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem + (size_t)STAGES * Cfg::STAGE_BYTES);
+    uint64_t* empty = full + STAGES;
 
     const int r = st->r, s = st->s;
     const double p = st->p, inv_p = st->inv_p;
     const int warp = threadIdx.x >> 5;
-    const int64_t row_tiles = (R + TMA_BOX_R - 1) / TMA_BOX_R;
+    const int64_t row_tiles = (R + BOX_R - 1) / BOX_R;
 
     if (threadIdx.x == 0) {
-        for (int i = 0; i < TMA_STAGES; ++i) {
+        for (int i = 0; i < STAGES; ++i) {
             tma::mbar_init(&full[i], 1);
             tma::mbar_init(&empty[i], 1);
         }
@@ -177,11 +197,16 @@ k_update_tma(const __grid_constant__ CUtensorMap map, const double* __restrict__
                 const int64_t strip = w % strips, chunk = w / strips;
                 const int64_t rt0 = chunk * chunk_tiles, rt1 = min(row_tiles, rt0 + (int64_t)chunk_tiles);
                 for (int64_t rt = rt0; rt < rt1; ++rt) {
+                    uint8_t* slot = smem + (size_t)stage * Cfg::STAGE_BYTES;
                     tma::mbar_wait(&empty[stage], phase ^ 1);
-                    tma::mbar_expect_tx(&full[stage], TMA_TILE_BYTES);
-                    tma::load_2d(tiles + (size_t)stage * TMA_TILE_DOUBLES, &map, &full[stage],
-                                 (int32_t)(strip * TMA_BOX_C), (int32_t)(rt * TMA_BOX_R));
-                    if (++stage == TMA_STAGES) {
+                    const uint32_t row_bytes = (rt == rt0) ? (uint32_t)(min((int64_t)TMA_BOX_C, ld - strip * TMA_BOX_C) * 8) : 0u;
+                    tma::mbar_expect_tx(&full[stage], Cfg::TILE_BYTES + Cfg::COL_BYTES + row_bytes);
+                    tma::load_2d(slot, &map, &full[stage], (int32_t)(strip * TMA_BOX_C), (int32_t)(rt * BOX_R));
+                    bulk_load_1d(slot + Cfg::TILE_BYTES, col + rt * BOX_R, Cfg::COL_BYTES, &full[stage]);
+                    if (row_bytes)
+                        bulk_load_1d(slot + Cfg::TILE_BYTES + Cfg::COL_PAD, T + (int64_t)r * ld + strip * TMA_BOX_C,
+                                     row_bytes, &full[stage]);
+                    if (++stage == STAGES) {
                         stage = 0;
                         phase ^= 1;
                     }
@@ -205,31 +230,28 @@ k_update_tma(const __grid_constant__ CUtensorMap map, const double* __restrict__
         const int64_t j = strip * TMA_BOX_C + cp;
         const bool sx = (j == s), sy = (j + 1 == s);
         double qx = 0.0, qy = 0.0;
-        if (j < C) {
-            const double2 rv = *reinterpret_cast<const double2*>(T + (int64_t)r * ld + j);
-            qx = sx ? inv_p : rv.x / p;
-            qy = sy ? inv_p : rv.y / p;
-        }
         for (int64_t rt = rt0; rt < rt1; ++rt) {
-            const int64_t i0 = rt * TMA_BOX_R;
-            double c[TMA_BOX_R / 2];
-#pragma unroll
-            for (int k = 0; k < TMA_BOX_R / 2; ++k) {
-                const int64_t i = i0 + 2 * k + rpar;
-                c[k] = i < R ? col[i] : 0.0;
-            }
+            const int64_t i0 = rt * BOX_R;
+            uint8_t* slot = smem + (size_t)stage * Cfg::STAGE_BYTES;
+            double* tile = reinterpret_cast<double*>(slot);
+            const double* cs = reinterpret_cast<const double*>(slot + Cfg::TILE_BYTES);
             tma::mbar_wait(&full[stage], phase);
-            double* tile = tiles + (size_t)stage * TMA_TILE_DOUBLES;
+            if (rt == rt0 && j < ld) {
+                const double2 rv = *reinterpret_cast<const double2*>(slot + Cfg::TILE_BYTES + Cfg::COL_PAD + cp * 8);
+                qx = sx ? inv_p : rv.x / p;
+                qy = sy ? inv_p : rv.y / p;
+            }
 #pragma unroll
-            for (int k = 0; k < TMA_BOX_R / 2; ++k) {
+            for (int k = 0; k < BOX_R / 2; ++k) {
                 const int lr = 2 * k + rpar;
                 if (i0 + lr != r) {
+                    const double c = cs[lr];
                     double2* cell = reinterpret_cast<double2*>(tile + lr * TMA_BOX_C + cp);
                     double2 v = *cell;
                     if (sx) v.x = 0.0;
                     if (sy) v.y = 0.0;
-                    v.x = __fma_rn(-c[k], qx, v.x);
-                    v.y = __fma_rn(-c[k], qy, v.y);
+                    v.x = __fma_rn(-c, qx, v.x);
+                    v.y = __fma_rn(-c, qy, v.y);
                     *cell = v;
                 }
             }
@@ -239,13 +261,13 @@ k_update_tma(const __grid_constant__ CUtensorMap map, const double* __restrict__
                 tma::store_2d(&map, tile, (int32_t)(strip * TMA_BOX_C), (int32_t)i0);
                 tma::store_commit();
                 ++issued;
-                tma::store_wait_read<TMA_STORE_LAG>();
-                while (released < issued - TMA_STORE_LAG) {
-                    tma::mbar_arrive(&empty[released % TMA_STAGES]);
+                tma::store_wait_read<STORE_LAG>();
+                while (released < issued - STORE_LAG) {
+                    tma::mbar_arrive(&empty[released % STAGES]);
                     ++released;
                 }
             }
-            if (++stage == TMA_STAGES) {
+            if (++stage == STAGES) {
                 stage = 0;
                 phase ^= 1;
             }

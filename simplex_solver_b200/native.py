@@ -34,7 +34,7 @@ EXPORTS = [
     "b200lp_run", "b200lp_solve", "b200lp_select_entering", "b200lp_ratio_test", "b200lp_pivot",
     "b200lp_shard_candidate", "b200lp_shard_pivot", "b200lp_shard_state", "b200lp_shard_reset",
     "b200lp_read_history", "b200lp_solve_batched", "b200lp_time_update", "b200lp_build_dense",
-    "b200lp_set_snapshots", "b200lp_profile_loop",
+    "b200lp_set_snapshots", "b200lp_profile_loop", "b200lp_use_own_stream",
 ]
 
 _f64p = C.POINTER(C.c_double)
@@ -105,6 +105,7 @@ def lib():
                 L.b200lp_destroy.argtypes = [C.c_void_p]
                 L.b200lp_set_stream.argtypes = [C.c_void_p, C.c_void_p]
                 L.b200lp_synchronize.argtypes = [C.c_void_p]
+                L.b200lp_use_own_stream.argtypes = [C.c_void_p]
                 L.b200lp_solve_dense.argtypes = [C.c_void_p, C.POINTER(Problem), C.POINTER(Opts), C.POINTER(Result)]
                 L.b200lp_build_dense.argtypes = [C.c_void_p, C.POINTER(Problem)]
                 L.b200lp_set_snapshots.argtypes = [C.c_void_p, C.c_void_p, C.c_int64]
@@ -189,8 +190,12 @@ class Solver:
             pass
 
     # ---- streams ------------------------------------------------------------------------------------
-    def set_stream(self, cuda_stream: int | None):
-        check(lib().b200lp_set_stream(self._h, C.c_void_p(cuda_stream or 0)))
+    def set_stream(self, cuda_stream: int):
+        """Run on the caller's stream (e.g. torch.cuda.current_stream().cuda_stream; 0 = legacy default stream)."""
+        check(lib().b200lp_set_stream(self._h, C.c_void_p(int(cuda_stream))))
+
+    def use_own_stream(self):
+        check(lib().b200lp_use_own_stream(self._h))
 
     def synchronize(self):
         check(lib().b200lp_synchronize(self._h))

@@ -44,7 +44,7 @@ class CudaShardEngine:
         self.cand = torch.zeros(self.R + 2, dtype=torch.float64, device=f"cuda:{device}")
 
     def new_buffer(self, world):
-        return self.torch.zeros(world * (self.R + 2), dtype=torch.float64, device=f"cuda:{self.device}")
+        return self.torch.zeros(world * (self.R + 2), dtype=self.torch.float64, device=f"cuda:{self.device}")
 
     def reset(self, max_pivots):
         self.solver.shard_reset(max_pivots)

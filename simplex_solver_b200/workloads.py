@@ -62,15 +62,16 @@ def batched_small_lps(start: int, count: int, m: int = 20, n: int = 30, base_see
         cb[unb] = -cb[unb]  # maximise c'x == minimise -c'x
         slack = np.where(ob == LE, s, np.where(ob == GE, -s, 0.0))
         bb = np.einsum("kij,kj->ki", Ab, x0) + slack
-        inf = gidx % 100 == 0
-        Ab[inf, 0, :] = 0.0
-        Ab[inf, 0, 0] = 1.0
-        bb[inf, 0] = 5.0
-        ob[inf, 0] = LE
-        Ab[inf, 1, :] = 0.0
-        Ab[inf, 1, 0] = 1.0
-        bb[inf, 1] = 10.0
-        ob[inf, 1] = GE
+        if m >= 2:  # the infeasible pair needs two rows
+            inf = gidx % 100 == 0
+            Ab[inf, 0, :] = 0.0
+            Ab[inf, 0, 0] = 1.0
+            bb[inf, 0] = 5.0
+            ob[inf, 0] = LE
+            Ab[inf, 1, :] = 0.0
+            Ab[inf, 1, 0] = 1.0
+            bb[inf, 1] = 10.0
+            ob[inf, 1] = GE
         A[done:done + k] = Ab[:k]
         b[done:done + k] = bb[:k]
         c[done:done + k] = cb[:k]

@@ -206,10 +206,13 @@ def test_config4_full_size_properties(solver):
     exp_col = -(col * inv_p)
     exp_col[r] = inv_p
     assert torch.equal(Tt[:, s], exp_col)
-    exp_row = rowr / p
+    # torch turns "tensor / python_scalar" into a multiplication by the reciprocal; divide by a device tensor to get
+    # the IEEE division the kernel performs
+    p_dev = col[r].clone()
+    exp_row = rowr / p_dev
     exp_row[s] = inv_p
     assert torch.equal(Tt[r, : n + 1], exp_row)
-    q = rowr[7:11] / p
+    q = rowr[7:11] / p_dev
     exp_some = torch.stack([torch.addcmul(some[k], -col[5 + k], q) for k in range(4)])  # not fused: 1 ulp slack
     assert torch.allclose(Tt[5:9, 7:11], exp_some, rtol=1e-15, atol=1e-15)
     zexp = z0 - col[m].item() * (rhs[r].item() / p)
