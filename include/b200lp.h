@@ -59,6 +59,13 @@ extern "C" {
 #define B200LP_UPDATE_LDG 1 /* 128-bit vectorised global loads/stores, register resident            */
 #define B200LP_UPDATE_TMA 2 /* cp.async.bulk.tensor tiles staged through shared memory (mbarrier ring) */
 
+/* loop drivers */
+#define B200LP_LOOP_LAUNCHES 0 /* three plain launches per pivot                                              */
+#define B200LP_LOOP_GRAPH 1    /* the iteration replayed as a CUDA graph                                       */
+#define B200LP_LOOP_AUTO 2     /* default: tableaux that fit the chip's shared memory (<= ~29 MB) run in ONE  */
+                               /* persistent cooperative kernel, SM-sharded and shared-memory resident, with  */
+                               /* one grid barrier per pivot; larger ones use the graph                       */
+
 /* error codes */
 #define B200LP_OK 0
 #define B200LP_E_INVALID (-1)
@@ -71,12 +78,13 @@ typedef struct b200lp_solver b200lp_solver;
 typedef struct b200lp_opts {
     int32_t rule;           /* B200LP_RULE_*                                                            */
     int32_t update_variant; /* B200LP_UPDATE_*                                                          */
-    int64_t max_pivots;     /* pivot budget of the call (status LIMIT when exhausted)                   */
+    int64_t max_pivots;     /* pivot budget of the call (status LIMIT when exhausted); the default      */
+                            /* (>= 2^40) means "automatic": 200 * (rows + columns) + 10000              */
     double eps_cost;        /* a reduced cost d_j enters only if d_j < -eps_cost                        */
     double eps_pivot;       /* a column entry takes part in the ratio test only if > eps_pivot          */
     double eps_feas;        /* phase 1 ends infeasible if the sum of artificials exceeds eps_feas       */
     int32_t check_every;    /* pivots enqueued between two host reads of the device status (0: default) */
-    int32_t use_graph;      /* 1: replay the iteration as a CUDA graph (default), 0: plain launches     */
+    int32_t loop_mode;      /* B200LP_LOOP_*: how the device-resident loop is driven                     */
 } b200lp_opts;
 
 /* min c'x  s.t.  A_i x (ops_i) b_i,  x >= 0.   A is m x n row-major with row stride lda. */

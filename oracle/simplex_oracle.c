@@ -332,20 +332,43 @@ static int orc_drive_out(orc_tableau *t, const orc_opts *o, orc_result *res, dou
     return ORC_OPT;
 }
 
+/* Pivot budget.  max_pivots >= 2^40 means "automatic": 200 * (m + C) + 10000 pivots, and -- because Dantzig's
+ * rule with lowest-id tie-breaking can cycle on degenerate problems (Beale's example does) -- a phase that
+ * exhausts an AUTOMATIC budget under Dantzig continues from the current basis under Bland's rule, which cannot
+ * cycle, with one more budget.  An explicit budget is honoured as given (status LIMIT).                       */
+#define ORC_AUTO_BUDGET ((int64_t)1 << 40)
+static int64_t orc_auto_cap(int64_t m, int64_t C) { return 200 * (m + C) + 10000; }
+
+static int orc_run_phase_fb(orc_tableau *t, int64_t obj_row, orc_opts *o, int is_auto, int64_t cap, orc_result *res,
+                            double *col) {
+    int st = orc_run_phase(t, obj_row, o, res, col);
+    if (st == ORC_LIMIT && is_auto && o->rule == ORC_RULE_DANTZIG) {
+        o->rule = ORC_RULE_BLAND;
+        o->max_pivots += cap;
+        st = orc_run_phase(t, obj_row, o, res, col);
+    }
+    return st;
+}
+
 /* Two-phase driver on a built tableau.  fun = -T[m][C-1] (objective of the minimisation form).         */
-ORC_EXPORT int orc_solve(orc_tableau *t, const orc_opts *o, orc_result *res) {
+ORC_EXPORT int orc_solve(orc_tableau *t, const orc_opts *o_in, orc_result *res) {
     double *col = (double *)malloc((size_t)t->R * sizeof(double));
+    orc_opts oo = *o_in;
+    orc_opts *o = &oo;
+    const int is_auto = o_in->max_pivots >= ORC_AUTO_BUDGET;
+    const int64_t cap = is_auto ? orc_auto_cap(t->m, t->C) : o_in->max_pivots;
+    o->max_pivots = cap;
     int st = ORC_OPT;
     res->n_pivots = 0;
     res->n_phase1 = 0;
     if (t->n_obj == 2) {
-        st = orc_run_phase(t, t->m + 1, o, res, col);
+        st = orc_run_phase_fb(t, t->m + 1, o, is_auto, cap, res, col);
         if (st == ORC_UNBOUNDED) st = ORC_NUMERICAL; /* w is bounded below by 0 */
         if (st == ORC_OPT && t->T[(t->m + 1) * t->ld + t->C - 1] < -o->eps_feas) st = ORC_INFEASIBLE;
         if (st == ORC_OPT) st = orc_drive_out(t, o, res, col);
         res->n_phase1 = res->n_pivots;
     }
-    if (st == ORC_OPT) st = orc_run_phase(t, t->m, o, res, col);
+    if (st == ORC_OPT) st = orc_run_phase_fb(t, t->m, o, is_auto, cap, res, col);
     free(col);
     res->status = st;
     res->fun = -t->T[t->m * t->ld + t->C - 1];

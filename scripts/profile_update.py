@@ -13,5 +13,5 @@ s = native.Solver(0)
 T = torch.empty(R * R, dtype=torch.float64, device="cuda:0")
 s.attach(T.data_ptr(), R - 1, 1, R, R, R - 1, 2 * R - 2, keep=T)
 s.generate(4, R - 1, 0)
-r = s.run(native.make_opts(rule=native.RULE_BLAND, max_pivots=6, update_variant=variant, check_every=6, use_graph=False))
+r = s.run(native.make_opts(rule=native.RULE_BLAND, max_pivots=6, update_variant=variant, check_every=6, loop_mode=native.LOOP_LAUNCHES))
 print(r["n_pivots"], r["device_ms"])

@@ -20,6 +20,7 @@
 #include "common.cuh"
 #include "kernels_batched.cuh"
 #include "kernels_build.cuh"
+#include "kernels_onchip.cuh"
 #include "kernels_pick.cuh"
 #include "kernels_update.cuh"
 
@@ -121,6 +122,10 @@ struct b200lp_solver {
     DevBuf<int8_t> sops;
     DevBuf<int32_t> sstatus, snpiv, slog;
 
+    // on-chip persistent loop: exchange buffer and grid-barrier counter
+    DevBuf<double> xbuf;
+    DevBuf<unsigned long long> gbar;
+
     // TMA descriptor of the current tableau
     CUtensorMap tmap;
     const double* tmap_T = nullptr;
@@ -153,7 +158,7 @@ B200LP_API void b200lp_default_opts(b200lp_opts* o) {
     o->eps_pivot = 1e-9;
     o->eps_feas = 1e-7;
     o->check_every = 0;
-    o->use_graph = 1;
+    o->loop_mode = B200LP_LOOP_AUTO;
 }
 
 B200LP_API int b200lp_create(b200lp_solver** out, int device) {
@@ -185,6 +190,8 @@ B200LP_API int b200lp_create(b200lp_solver** out, int device) {
     CKR(s->sfun.ensure(1));
     CK(cudaFuncSetAttribute(k_update_tma<TMA_BOX_R, TMA_STAGES, TMA_STORE_LAG, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                             (int)TmaCfg<TMA_BOX_R, TMA_STAGES>::SMEM_BYTES));
+    CK(cudaFuncSetAttribute(k_solve_onchip, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ONCHIP_SMEM_MAX));
+    CKR(s->gbar.ensure(1));
     CK(cudaStreamSynchronize(s->stream));
     *out = s;
     return 0;
@@ -216,6 +223,8 @@ B200LP_API int b200lp_destroy(b200lp_solver* s) {
     s->sstatus.release();
     s->snpiv.release();
     s->slog.release();
+    s->xbuf.release();
+    s->gbar.release();
     if (s->st_host) cudaFreeHost(s->st_host);
     cudaEventDestroy(s->ev0);
     cudaEventDestroy(s->ev1);
@@ -555,11 +564,71 @@ static int get_graph(b200lp_solver* s, const b200lp_opts* o, int64_t obj_row, in
     return 0;
 }
 
+struct OnchipPlan {
+    int G = 0, stride = 0;
+    size_t smem = 0;
+};
+
+static bool onchip_plan(const b200lp_solver* s, OnchipPlan* plan) {
+    if (s->C < 2 || s->snaps) return false;
+    const int64_t G = std::min<int64_t>(s->sm_count, s->C - 1);
+    const int64_t wmax = (s->C - 1 + G - 1) / G;
+    int64_t stride = wmax + 1;
+    if ((stride & 1) == 0) ++stride;
+    const size_t smem = (size_t)(s->R * stride + s->R + stride) * 8 + (size_t)(s->R + wmax) * 4 + 64;
+    if (smem > ONCHIP_SMEM_MAX) return false;
+    plan->G = (int)G;
+    plan->stride = (int)stride;
+    plan->smem = smem;
+    return true;
+}
+
+// One phase of the loop as ONE persistent cooperative kernel (kernels_onchip.cuh).
+static int run_onchip(b200lp_solver* s, const b200lp_opts* o, int64_t obj_row, const OnchipPlan& plan, DevState* final_state) {
+    CKR(launch_flush(s));
+    const size_t xdoubles = (size_t)2 * plan.G * (s->R + 2);
+    CKR(s->xbuf.ensure(xdoubles));
+    CK(cudaMemsetAsync(s->gbar.p, 0, sizeof(unsigned long long), s->stream));
+    OnchipParams P;
+    P.T = s->T;
+    P.R = s->R;
+    P.m = s->m;
+    P.C = s->C;
+    P.ld = s->ld;
+    P.obj_row = obj_row;
+    P.rowlab = s->rowlab.p;
+    P.collab = s->collab.p;
+    P.art_base = s->art_base;
+    P.rule = o->rule;
+    P.eps_cost = o->eps_cost;
+    P.eps_pivot = o->eps_pivot;
+    P.st = s->st.p;
+    P.xbuf = s->xbuf.p;
+    P.barrier = s->gbar.p;
+    P.h_row = s->h_row.p;
+    P.h_col = s->h_col.p;
+    P.h_enter = s->h_enter.p;
+    P.h_leave = s->h_leave.p;
+    P.hist_cap = s->hist_cap;
+    P.stride = plan.stride;
+    void* args[] = {&P};
+    CK(cudaLaunchCooperativeKernel((void*)k_solve_onchip, dim3(plan.G), dim3(ONCHIP_THREADS), args, plan.smem, s->stream));
+    s->launches++;
+    CK(cudaMemcpyAsync(&s->st_host[0], s->st.p, sizeof(DevState), cudaMemcpyDeviceToHost, s->stream));
+    CK(cudaStreamSynchronize(s->stream));
+    *final_state = s->st_host[0];
+    return 0;
+}
+
 // Runs chunks of iterations until the device reports done.  mode 0: pricing loop on obj_row; mode 1: drive-out.
 static int run_loop(b200lp_solver* s, const b200lp_opts* o, int64_t obj_row, int mode, DevState* final_state) {
+    if (mode == 0 && o->loop_mode == B200LP_LOOP_AUTO) {
+        OnchipPlan plan;
+        if (onchip_plan(s, &plan)) return run_onchip(s, o, obj_row, plan, final_state);
+    }
     int iters = o->check_every > 0 ? o->check_every : default_check_every(s);
     if (mode == 1) iters = std::min(iters, 8);
-    const bool use_graph = o->use_graph && mode == 0 && s->stream != (cudaStream_t)0;
+    const bool use_graph = o->loop_mode != B200LP_LOOP_LAUNCHES && mode == 0 && s->stream != (cudaStream_t)0;
     if (use_graph) CKR(get_graph(s, o, obj_row, iters));
     const int per_iter = s->snaps ? 4 : 3;
     int slot = 0;
@@ -588,6 +657,20 @@ static int run_loop(b200lp_solver* s, const b200lp_opts* o, int64_t obj_row, int
     // the newest copy is at least as recent as the one that reported done
     const DevState& a = s->st_host[slot];
     *final_state = a.done ? a : s->st_host[slot ^ 1];
+    return 0;
+}
+
+// run_loop for a pricing phase, with the Dantzig -> Bland continuation described above.  `o` is the call's private
+// copy of the options (its rule may be switched), `budget` the current cap held in DevState.max_pivots.
+static int run_phase_fb(b200lp_solver* s, b200lp_opts* o, int64_t obj_row, bool is_auto, int64_t cap, int64_t* budget,
+                        DevState* fin) {
+    CKR(run_loop(s, o, obj_row, 0, fin));
+    if (fin->status == B200LP_STATUS_LIMIT && is_auto && o->rule == B200LP_RULE_DANTZIG) {
+        o->rule = B200LP_RULE_BLAND;
+        *budget += cap;
+        CKR(launch_reset(s, *budget, true));
+        CKR(run_loop(s, o, obj_row, 0, fin));
+    }
     return 0;
 }
 
@@ -634,11 +717,20 @@ B200LP_API int b200lp_read_tableau(b200lp_solver* s, double* T_host) {
     return 0;
 }
 
+// Pivot budget (same rule as oracle/simplex_oracle.c).  max_pivots >= 2^40 means "automatic": 200 * (m + C) + 10000
+// pivots, and -- because Dantzig's rule with lowest-id tie-breaking can cycle on degenerate problems -- a phase that
+// exhausts an AUTOMATIC budget under Dantzig continues from the current basis under Bland's rule (which cannot cycle)
+// with one more budget.  A device loop must always terminate; the reference bounds its solver by wall clock instead
+// (time_limit = 10 s, solver_controller.py:76).  An explicit budget is honoured as given (status LIMIT).
+static const int64_t AUTO_BUDGET = (int64_t)1 << 40;
+static int64_t auto_cap(int64_t m, int64_t C) { return 200 * (m + C) + 10000; }
+
 static int check_opts(const b200lp_opts* o) {
     if (!o) return fail(B200LP_E_INVALID, "opts is NULL");
     if (o->rule != B200LP_RULE_DANTZIG && o->rule != B200LP_RULE_BLAND) return fail(B200LP_E_INVALID, "unknown rule %d", o->rule);
     if (o->update_variant < 0 || o->update_variant > 2) return fail(B200LP_E_INVALID, "unknown update variant %d", o->update_variant);
     if (o->max_pivots < 0) return fail(B200LP_E_INVALID, "max_pivots < 0");
+    if (o->loop_mode < 0 || o->loop_mode > 2) return fail(B200LP_E_INVALID, "unknown loop_mode %d", o->loop_mode);
     return 0;
 }
 
@@ -648,11 +740,15 @@ B200LP_API int b200lp_run(b200lp_solver* s, const b200lp_opts* o, int64_t obj_ro
     if (obj_row < s->m || obj_row >= s->R) return fail(B200LP_E_INVALID, "obj_row %lld is not an objective row", (long long)obj_row);
     CKR(set_device(s));
     const int64_t l0 = s->launches;
-    CKR(ensure_hist(s, std::min<int64_t>(o->max_pivots, r && r->hist_cap > 0 ? r->hist_cap : 16)));
-    CKR(launch_reset(s, o->max_pivots, false));
+    b200lp_opts oo = *o;
+    const bool is_auto = o->max_pivots >= AUTO_BUDGET;
+    const int64_t cap = is_auto ? auto_cap(s->m, s->C) : o->max_pivots;
+    int64_t budget = cap;
+    CKR(ensure_hist(s, std::min<int64_t>(budget, r && r->hist_cap > 0 ? r->hist_cap : 16)));
+    CKR(launch_reset(s, budget, false));
     DevState fin;
     CK(cudaEventRecord(s->ev0, s->stream));
-    CKR(run_loop(s, o, obj_row, 0, &fin));
+    CKR(run_phase_fb(s, &oo, obj_row, is_auto, cap, &budget, &fin));
     CKR(launch_flush(s));
     CK(cudaEventRecord(s->ev1, s->stream));
     CK(cudaStreamSynchronize(s->stream));
@@ -675,15 +771,19 @@ B200LP_API int b200lp_solve(b200lp_solver* s, const b200lp_opts* o, b200lp_resul
     CKR(check_opts(o));
     CKR(set_device(s));
     const int64_t l0 = s->launches;
-    CKR(ensure_hist(s, std::min<int64_t>(o->max_pivots, r && r->hist_cap > 0 ? r->hist_cap : 16)));
-    CKR(launch_reset(s, o->max_pivots, false));
+    b200lp_opts oo = *o;
+    const bool is_auto = o->max_pivots >= AUTO_BUDGET;
+    const int64_t cap = is_auto ? auto_cap(s->m, s->C) : o->max_pivots;
+    int64_t budget = cap;
+    CKR(ensure_hist(s, std::min<int64_t>(budget, r && r->hist_cap > 0 ? r->hist_cap : 16)));
+    CKR(launch_reset(s, budget, false));
     DevState fin;
     memset(&fin, 0, sizeof(fin));
     int status = B200LP_STATUS_OPTIMAL;
     int64_t n_phase1 = 0;
     CK(cudaEventRecord(s->ev0, s->stream));
     if (s->n_obj == 2) {
-        CKR(run_loop(s, o, s->m + 1, 0, &fin));
+        CKR(run_phase_fb(s, &oo, s->m + 1, is_auto, cap, &budget, &fin));
         status = fin.status;
         if (status == B200LP_STATUS_UNBOUNDED) status = B200LP_STATUS_NUMERICAL;
         if (status == B200LP_STATUS_OPTIMAL) {
@@ -694,15 +794,15 @@ B200LP_API int b200lp_solve(b200lp_solver* s, const b200lp_opts* o, b200lp_resul
             if (w < -o->eps_feas) status = B200LP_STATUS_INFEASIBLE;
         }
         if (status == B200LP_STATUS_OPTIMAL) {
-            CKR(launch_reset(s, o->max_pivots, true));
-            CKR(run_loop(s, o, s->m, 1, &fin));
+            CKR(launch_reset(s, budget, true));
+            CKR(run_loop(s, &oo, s->m, 1, &fin));
             status = fin.status;
         }
         n_phase1 = fin.n_pivots;
     }
     if (status == B200LP_STATUS_OPTIMAL) {
-        CKR(launch_reset(s, o->max_pivots, true));
-        CKR(run_loop(s, o, s->m, 0, &fin));
+        CKR(launch_reset(s, budget, true));
+        CKR(run_phase_fb(s, &oo, s->m, is_auto, cap, &budget, &fin));
         status = fin.status;
     }
     CKR(launch_flush(s));
@@ -1096,7 +1196,8 @@ B200LP_API int b200lp_solve_batched(b200lp_solver* s, int64_t B, int64_t m, int6
     P.n = (int32_t)n;
     P.ld = (int32_t)ld;
     P.rule = o->rule;
-    P.max_pivots = (int32_t)std::min<int64_t>(o->max_pivots, 0x7fffffff);
+    P.auto_budget = o->max_pivots >= AUTO_BUDGET ? 1 : 0;
+    P.max_pivots = (int32_t)std::min<int64_t>(o->max_pivots, 0x3fffffff);  // automatic budgets are sized per LP in the kernel
     P.log_cap = (int32_t)(dlog ? log_cap : 0);
     P.eps_cost = o->eps_cost;
     P.eps_pivot = o->eps_pivot;

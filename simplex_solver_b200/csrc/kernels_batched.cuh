@@ -21,6 +21,7 @@ struct BatchedParams {
     int32_t ld;         // odd row stride of the shared-memory tableau, >= n + m + 1
     int32_t rule;
     int32_t max_pivots;
+    int32_t auto_budget;  // 1: budget = 200 * (m + C) + 10000 per LP, with the Dantzig -> Bland continuation
     int32_t log_cap;
     double eps_cost, eps_pivot, eps_feas;
     const double* A;
@@ -262,13 +263,28 @@ __global__ void __launch_bounds__(256) k_solve_batched(const BatchedParams P) {
         for (int e = lane; e < 2 * P.log_cap; e += 32) run.log[e] = -1;
     __syncwarp();
     int st = 0;
+    int rule = P.rule;
+    const int cap = P.auto_budget ? 200 * (m + C) + 10000 : P.max_pivots;
+    run.max_pivots = cap;
     if (n_obj == 2) {
-        st = wlp_run_phase(w, m + 1, P.rule, P.eps_cost, P.eps_pivot, run, lane);
+        st = wlp_run_phase(w, m + 1, rule, P.eps_cost, P.eps_pivot, run, lane);
+        if (st == 1 && P.auto_budget && rule == 0) {  // Dantzig stalled: continue under Bland (cannot cycle)
+            rule = 1;
+            run.max_pivots += cap;
+            st = wlp_run_phase(w, m + 1, rule, P.eps_cost, P.eps_pivot, run, lane);
+        }
         if (st == 3) st = 4;
         if (st == 0 && w.T[(m + 1) * ld + C - 1] < -P.eps_feas) st = 2;
         if (st == 0) st = wlp_drive_out(w, P.eps_pivot, run, lane);
     }
-    if (st == 0) st = wlp_run_phase(w, m, P.rule, P.eps_cost, P.eps_pivot, run, lane);
+    if (st == 0) {
+        st = wlp_run_phase(w, m, rule, P.eps_cost, P.eps_pivot, run, lane);
+        if (st == 1 && P.auto_budget && rule == 0) {
+            rule = 1;
+            run.max_pivots += cap;
+            st = wlp_run_phase(w, m, rule, P.eps_cost, P.eps_pivot, run, lane);
+        }
+    }
 
     // ---- results ----
     if (P.x) {

@@ -1,0 +1,227 @@
+// kernels_onchip.cuh -- the pivot loop for tableaux that fit the chip's aggregate shared memory (~30 MB):
+// one persistent cooperative kernel, the tableau column-sharded over the SMs and RESIDENT IN SHARED MEMORY for the
+// whole phase, ONE grid barrier per pivot.  This is the path of BASELINE config 2 (1024 x 1024, 8.4 MB), which is
+// latency-bound, not HBM-bound: three launches per pivot cost ~16 us, this loop ~3-4 us.
+//
+// Layout (the multi-GPU column sharding of sharded.py, applied across SMs): CTA g owns columns [lo_g, hi_g) of EVERY
+// row plus its own replica of the right-hand-side column and of the row labels.  Per pivot:
+//   1. local argmin over the CTA's slice of the objective row;
+//   2. publish [reduced cost, variable id, candidate column (R doubles)] to a global exchange buffer (L2 resident);
+//   3. grid barrier (the only one);
+//   4. every CTA reads the G headers, takes the same decision (total order), copies the winner's column, runs the
+//      ratio test redundantly on its RHS replica, scales its slice of the pivot row and applies the rank-1 update
+//      to its columns in shared memory.
+// No pivot-row exchange is needed under column sharding, and the ratio test needs no second reduction because the RHS
+// is replicated.  Arithmetic and tie-breaking are those of DESIGN.md section 2: bit-identical to the oracle.
+#pragma once
+#include "common.cuh"
+
+namespace b200lp {
+
+constexpr int ONCHIP_THREADS = 256;
+// shared-memory budget: the 227 KB a CTA can opt in to, minus the kernel's static shared memory
+constexpr size_t ONCHIP_SMEM_MAX = 232448 - 1024;
+
+struct OnchipParams {
+    double* T;           // global tableau (loaded at start, written back at the end)
+    int64_t R, m, C, ld;
+    int64_t obj_row;
+    int32_t* rowlab;     // global labels (read at start, written back at the end)
+    int32_t* collab;
+    int32_t art_base;
+    int32_t rule;        // 0 Dantzig, 1 Bland
+    double eps_cost, eps_pivot;
+    DevState* st;
+    double* xbuf;        // exchange: 2 x G x (R + 2) doubles
+    unsigned long long* barrier;  // monotonic arrival counter (zeroed before the launch)
+    int32_t* h_row;
+    int32_t* h_col;
+    int32_t* h_enter;
+    int32_t* h_leave;
+    int64_t hist_cap;
+    int32_t stride;      // odd row stride of the shared-memory slice, >= widest slice + 1
+};
+
+// Grid barrier on a monotonic arrival counter (the kernel is launched cooperatively, so all CTAs are resident).
+// One thread per CTA arrives with a release reduction (no return value to wait for) and polls with acquire loads.
+// (A flag-per-CTA all-to-all exchange without a counter was measured slower on B200: 148 x 148 acquire-polling
+// threads cost more than one poller per CTA plus a separate read of the headers.)
+__device__ __forceinline__ void grid_barrier(unsigned long long* counter, unsigned long long target) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        asm volatile("red.release.gpu.global.add.u64 [%0], 1;" ::"l"(counter) : "memory");
+        unsigned long long v;
+        do {
+            asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(counter) : "memory");
+        } while (v < target);
+    }
+    __syncthreads();
+}
+
+__global__ void __launch_bounds__(ONCHIP_THREADS, 1) k_solve_onchip(const OnchipParams P) {
+    extern __shared__ __align__(16) uint8_t smem_onchip[];
+    __shared__ Key sk[ONCHIP_THREADS / 32];
+    __shared__ Key bc;
+    const int G = gridDim.x, g = blockIdx.x, tid = threadIdx.x;
+    const int64_t R = P.R, m = P.m, C = P.C;
+    const int stride = P.stride;
+    const int64_t lo = (C - 1) * g / G, hi = (C - 1) * (g + 1) / G;
+    const int wl = (int)(hi - lo);  // local real columns; local column wl = RHS replica
+
+    double* Tl = reinterpret_cast<double*>(smem_onchip);
+    double* colbuf = Tl + (size_t)R * stride;
+    double* qloc = colbuf + R;
+    int32_t* rl = reinterpret_cast<int32_t*>(qloc + stride);
+    int32_t* cl = rl + R;
+
+    // ---- load the slice ----
+    for (int64_t e = tid; e < R * (wl + 1); e += ONCHIP_THREADS) {
+        const int64_t i = e / (wl + 1);
+        const int j = (int)(e - i * (wl + 1));
+        Tl[i * stride + j] = P.T[i * P.ld + (j < wl ? lo + j : C - 1)];
+    }
+    for (int64_t i = tid; i < R; i += ONCHIP_THREADS) rl[i] = P.rowlab[i];
+    for (int j = tid; j < wl; j += ONCHIP_THREADS) cl[j] = P.collab[lo + j];
+    __syncthreads();
+
+    long long n_pivots = P.st->n_pivots;
+    const long long max_pivots = P.st->max_pivots;
+    int status = -1;
+    const int64_t xstride = R + 2;
+    unsigned long long bar_round = 0;
+
+    for (long long it = 0;; ++it) {
+        if (n_pivots >= max_pivots) {
+            status = 1;
+            break;
+        }
+        // ---- 1. local pricing ----
+        Key k = key_none();
+        for (int j = tid; j < wl; j += ONCHIP_THREADS) {
+            const int32_t lab = cl[j];
+            const double v = Tl[P.obj_row * stride + j];
+            if (lab < P.art_base && v < -P.eps_cost) {
+                Key c;
+                c.v = v;
+                c.lab = lab;
+                c.pos = j;
+                k = P.rule ? key_min<true>(k, c) : key_min<false>(k, c);
+            }
+        }
+        k = P.rule ? block_key_min<true>(k, sk) : block_key_min<false>(k, sk);
+        if (tid == 0) bc = k;
+        __syncthreads();
+        const Key mine = bc;
+        // ---- 2. publish the candidate ----
+        double* slot = P.xbuf + ((size_t)(it & 1) * G + g) * xstride;
+        if (tid == 0) {
+            slot[0] = mine.v;
+            slot[1] = mine.lab == B200LP_NO_LAB ? -1.0 : (double)mine.lab;
+        }
+        if (mine.lab != B200LP_NO_LAB)
+            for (int64_t i = tid; i < R; i += ONCHIP_THREADS) slot[2 + i] = Tl[i * stride + mine.pos];
+        // ---- 3. the grid barrier of this pivot ----
+        ++bar_round;
+        grid_barrier(P.barrier, bar_round * (unsigned long long)G);
+        // ---- 4. global decision (identical on every CTA) ----
+        k = key_none();
+        const double* xb = P.xbuf + (size_t)(it & 1) * G * xstride;
+        for (int b = tid; b < G; b += ONCHIP_THREADS) {
+            const double labd = __ldcg(xb + (size_t)b * xstride + 1);
+            if (labd >= 0.0) {
+                Key c;
+                c.v = __ldcg(xb + (size_t)b * xstride);
+                c.lab = (int32_t)labd;
+                c.pos = b;
+                k = P.rule ? key_min<true>(k, c) : key_min<false>(k, c);
+            }
+        }
+        k = P.rule ? block_key_min<true>(k, sk) : block_key_min<false>(k, sk);
+        if (tid == 0) bc = k;
+        __syncthreads();
+        const Key win = bc;
+        if (win.lab == B200LP_NO_LAB) {
+            status = 0;
+            break;
+        }
+        const double* wcol = xb + (size_t)win.pos * xstride + 2;
+        for (int64_t i = tid; i < R; i += ONCHIP_THREADS) colbuf[i] = __ldcg(wcol + i);
+        __syncthreads();
+        // ---- ratio test on the RHS replica ----
+        k = key_none();
+        for (int64_t i = tid; i < m; i += ONCHIP_THREADS) {
+            const int32_t lab = rl[i];
+            const double a = colbuf[i];
+            if (lab >= 0 && a > P.eps_pivot) {
+                Key c;
+                c.v = Tl[i * stride + wl] / a;
+                c.lab = lab;
+                c.pos = (int32_t)i;
+                k = key_min<false>(k, c);
+            }
+        }
+        k = block_key_min<false>(k, sk);
+        if (tid == 0) bc = k;
+        __syncthreads();
+        const int r = bc.pos;
+        if (r < 0) {
+            status = 3;
+            break;
+        }
+        const int s_local = (win.pos == g) ? mine.pos : -1;
+        const double p = colbuf[r];
+        const double inv_p = 1.0 / p;
+        for (int j = tid; j <= wl; j += ONCHIP_THREADS) qloc[j] = (j == s_local) ? inv_p : Tl[(int64_t)r * stride + j] / p;
+        __syncthreads();
+        // ---- rank-1 update of the local columns (thread = row, odd stride => conflict-free) ----
+        for (int64_t i = tid; i < R; i += ONCHIP_THREADS) {
+            if (i == r) continue;
+            const double nc = -colbuf[i];
+            double* row = Tl + i * stride;
+            for (int j = 0; j <= wl; ++j) {
+                const double t = (j == s_local) ? 0.0 : row[j];
+                row[j] = __fma_rn(nc, qloc[j], t);
+            }
+        }
+        for (int j = tid; j <= wl; j += ONCHIP_THREADS) Tl[(int64_t)r * stride + j] = qloc[j];
+        __syncthreads();
+        // ---- bookkeeping ----
+        if (tid == 0) {
+            const int32_t leave = rl[r];
+            rl[r] = win.lab;
+            if (s_local >= 0) cl[s_local] = leave;
+            if (n_pivots < P.hist_cap) {
+                if (g == 0) {
+                    P.h_row[n_pivots] = r;
+                    P.h_enter[n_pivots] = win.lab;
+                    P.h_leave[n_pivots] = leave;
+                }
+                if (s_local >= 0) P.h_col[n_pivots] = (int32_t)(lo + s_local);  // exactly one CTA owns the column
+            }
+        }
+        ++n_pivots;
+        __syncthreads();
+    }
+
+    // ---- write the slice, the labels and the state back ----
+    __syncthreads();
+    for (int64_t e = tid; e < R * (wl + 1); e += ONCHIP_THREADS) {
+        const int64_t i = e / (wl + 1);
+        const int j = (int)(e - i * (wl + 1));
+        if (j < wl) P.T[i * P.ld + lo + j] = Tl[i * stride + j];
+        else if (g == G - 1) P.T[i * P.ld + C - 1] = Tl[i * stride + j];
+    }
+    for (int j = tid; j < wl; j += ONCHIP_THREADS) P.collab[lo + j] = cl[j];
+    if (g == 0) {
+        for (int64_t i = tid; i < R; i += ONCHIP_THREADS) P.rowlab[i] = rl[i];
+        if (tid == 0) {
+            P.st->done = 1;
+            P.st->status = status;
+            P.st->have_pivot = 0;
+            P.st->pend = 0;
+            P.st->n_pivots = n_pivots;
+        }
+    }
+}
+
+}  // namespace b200lp

@@ -20,6 +20,7 @@ RULE_DANTZIG, RULE_BLAND = 0, 1
 STATUS_OPTIMAL, STATUS_LIMIT, STATUS_INFEASIBLE, STATUS_UNBOUNDED, STATUS_NUMERICAL = 0, 1, 2, 3, 4
 OP_LE, OP_GE, OP_EQ = 0, 1, 2
 UPDATE_AUTO, UPDATE_LDG, UPDATE_TMA = 0, 1, 2
+LOOP_LAUNCHES, LOOP_GRAPH, LOOP_AUTO = 0, 1, 2
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
@@ -46,7 +47,7 @@ class Opts(C.Structure):
     _fields_ = [
         ("rule", C.c_int32), ("update_variant", C.c_int32), ("max_pivots", C.c_int64),
         ("eps_cost", C.c_double), ("eps_pivot", C.c_double), ("eps_feas", C.c_double),
-        ("check_every", C.c_int32), ("use_graph", C.c_int32),
+        ("check_every", C.c_int32), ("loop_mode", C.c_int32),
     ]
 
 
@@ -147,7 +148,7 @@ def check(rc: int):
 
 
 def make_opts(rule=RULE_DANTZIG, max_pivots=None, eps_cost=1e-9, eps_pivot=1e-9, eps_feas=1e-7,
-              update_variant=UPDATE_AUTO, check_every=0, use_graph=True) -> Opts:
+              update_variant=UPDATE_AUTO, check_every=0, loop_mode=LOOP_AUTO, use_graph=None) -> Opts:
     o = Opts()
     lib().b200lp_default_opts(C.byref(o))
     o.rule = rule
@@ -156,7 +157,9 @@ def make_opts(rule=RULE_DANTZIG, max_pivots=None, eps_cost=1e-9, eps_pivot=1e-9,
     o.eps_cost, o.eps_pivot, o.eps_feas = eps_cost, eps_pivot, eps_feas
     o.update_variant = update_variant
     o.check_every = check_every
-    o.use_graph = 1 if use_graph else 0
+    if use_graph is not None:  # explicit multi-kernel loop: graph replay or plain launches
+        loop_mode = LOOP_GRAPH if use_graph else LOOP_LAUNCHES
+    o.loop_mode = loop_mode
     return o
 
 

@@ -32,7 +32,7 @@ def test_version_and_default_opts():
     assert L.b200lp_version() == 100
     o = native.make_opts()
     assert o.rule == native.RULE_DANTZIG and o.eps_cost == 1e-9 and o.eps_pivot == 1e-9 and o.eps_feas == 1e-7
-    assert o.max_pivots == 1 << 40 and o.use_graph == 1
+    assert o.max_pivots == 1 << 40 and o.loop_mode == native.LOOP_AUTO
 
 
 def test_struct_layouts_match_the_header():

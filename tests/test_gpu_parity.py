@@ -108,13 +108,16 @@ def test_dense_update_variants_agree(solver, oracle):
     cmin = to_min_form(c, mx)
     ref = oracle.solve_lp(A, b, cmin, ops, hist_cap=1 << 13)
     for variant in (native.UPDATE_LDG, native.UPDATE_TMA):
-        for graph in (True, False):
-            got = solver.solve_dense(A, b, cmin, ops, native.make_opts(update_variant=variant, use_graph=graph,
+        for mode in (native.LOOP_LAUNCHES, native.LOOP_GRAPH, native.LOOP_AUTO):
+            got = solver.solve_dense(A, b, cmin, ops, native.make_opts(update_variant=variant, loop_mode=mode,
                                                                      check_every=16), hist_cap=1 << 13)
-            assert got["n_pivots"] == ref["n_pivots"], (variant, graph)
+            assert got["n_pivots"] == ref["n_pivots"], (variant, mode)
             np.testing.assert_array_equal(got["piv_row"], ref["piv_row"])
-            assert_bit_equal(got["fun"], ref["fun"], f"variant {variant} graph {graph}")
-            assert_bit_equal(got["x"], ref["x"], f"variant {variant} graph {graph}")
+            np.testing.assert_array_equal(got["piv_col"], ref["piv_col"])
+            np.testing.assert_array_equal(got["enter_lab"], ref["enter_lab"])
+            np.testing.assert_array_equal(got["leave_lab"], ref["leave_lab"])
+            assert_bit_equal(got["fun"], ref["fun"], f"variant {variant} loop mode {mode}")
+            assert_bit_equal(got["x"], ref["x"], f"variant {variant} loop mode {mode}")
 
 
 # ---------------------------------------------------------------------------------------------------
@@ -147,14 +150,19 @@ def test_generated_tableau_and_single_phases_bit_exact(solver, oracle, shape):
         np.testing.assert_array_equal(cl, ot.collab)
 
 
-@pytest.mark.parametrize("variant", [native.UPDATE_LDG, native.UPDATE_TMA])
+@pytest.mark.parametrize("variant", [native.UPDATE_LDG, native.UPDATE_TMA, "onchip"])
 @pytest.mark.parametrize("rule", [native.RULE_BLAND, native.RULE_DANTZIG])
 def test_device_loop_fixed_budget_bit_exact(solver, oracle, rule, variant):
-    """Config 4 in miniature: a fixed pivot budget on a generated square tableau, Bland and Dantzig."""
+    """Config 4 in miniature: a fixed pivot budget on a generated square tableau, Bland and Dantzig, through the
+    multi-kernel graph loop (both update kernels) and through the on-chip persistent loop."""
     m, n, budget = 255, 255, 150
     T, ld = _device_tableau(solver, m, 1, n + 1, n, n + m)
     solver.generate(4, n, 0)
-    got = solver.run(native.make_opts(rule=rule, max_pivots=budget, update_variant=variant), hist_cap=budget)
+    if variant == "onchip":
+        o = native.make_opts(rule=rule, max_pivots=budget, loop_mode=native.LOOP_AUTO)
+    else:
+        o = native.make_opts(rule=rule, max_pivots=budget, update_variant=variant, loop_mode=native.LOOP_GRAPH)
+    got = solver.run(o, hist_cap=budget)
     ot = oracle.OracleTableau.generate(4, m, n)
     ref = ot.solve(oracle.make_opts(rule=rule, max_pivots=budget), hist_cap=budget)
     assert got["status"] == ref["status"] == 1 and got["n_pivots"] == ref["n_pivots"] == budget
@@ -324,3 +332,26 @@ def test_invalid_arguments_fail_loudly(solver):
     with pytest.raises(native.B200LPError):
         solver.solve_dense(np.zeros((1, 1)), np.zeros(1), np.zeros(1), np.zeros(1, dtype=np.int8),
                            native.make_opts(rule=9))
+
+
+def test_beale_cycling_example_terminates_like_the_oracle(solver, oracle):
+    """A degenerate LP that cycles under Dantzig: the device loop must stop (explicit budget -> LIMIT) or recover
+    (automatic budget -> Bland continuation), with the same pivots as the oracle, on every path."""
+    from tests.test_oracle_golden import BEALE_A, BEALE_B, BEALE_C
+    ops = np.zeros(3, dtype=np.int8)
+    for mode in (native.LOOP_AUTO, native.LOOP_GRAPH):
+        got = solver.solve_dense(BEALE_A, BEALE_B, BEALE_C, ops, native.make_opts(max_pivots=500, loop_mode=mode),
+                                 hist_cap=500)
+        ref = oracle.solve_lp(BEALE_A, BEALE_B, BEALE_C, ops, oracle.make_opts(max_pivots=500), hist_cap=500)
+        assert got["status"] == ref["status"] == native.STATUS_LIMIT and got["n_pivots"] == 500
+        np.testing.assert_array_equal(got["piv_col"], ref["piv_col"])
+    got = solver.solve_dense(BEALE_A, BEALE_B, BEALE_C, ops, hist_cap=1 << 14)
+    ref = oracle.solve_lp(BEALE_A, BEALE_B, BEALE_C, ops, hist_cap=1 << 14)
+    assert got["status"] == ref["status"] == 0 and got["n_pivots"] == ref["n_pivots"]
+    np.testing.assert_array_equal(got["enter_lab"], ref["enter_lab"])
+    assert_bit_equal(got["fun"], ref["fun"], "fun")
+    assert abs(got["fun"] + 1.25) < 1e-9
+    A3, b3, c3, o3 = (np.stack([a] * 5) for a in (BEALE_A, BEALE_B, BEALE_C, ops))
+    gb = solver.solve_batched(A3, b3, c3, o3)
+    assert (gb["status"] == 0).all() and (gb["n_pivots"] == ref["n_pivots"]).all()
+    assert_bit_equal(gb["fun"], np.full(5, ref["fun"]), "batched fun")

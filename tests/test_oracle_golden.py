@@ -127,3 +127,22 @@ def test_threads_do_not_change_bits(oracle):
     assert r1["n_pivots"] == r4["n_pivots"] and r1["fun"] == r4["fun"]
     np.testing.assert_array_equal(r1["piv_row"], r4["piv_row"])
     np.testing.assert_array_equal(r1["x"], r4["x"])
+
+
+BEALE_A = np.array([[0.25, -8.0, -1.0, 9.0], [0.5, -12.0, -0.5, 3.0], [0.0, 0.0, 1.0, 0.0]])
+BEALE_B = np.array([0.0, 0.0, 1.0])
+BEALE_C = np.array([-0.75, 20.0, -0.5, 6.0])
+
+
+def test_beale_cycling_example_terminates(oracle):
+    """Beale's degenerate LP cycles under Dantzig's rule with lowest-id tie-breaking.  An explicit budget ends in
+    LIMIT; the automatic budget continues under Bland's rule and reaches the optimum z* = -1.25 (HiGHS: -1.25)."""
+    ops = np.zeros(3, dtype=np.int8)
+    r = oracle.solve_lp(BEALE_A, BEALE_B, BEALE_C, ops, oracle.make_opts(rule=0, max_pivots=1000), hist_cap=16)
+    assert r["status"] == oracle.LIMIT and r["n_pivots"] == 1000
+    assert list(r["piv_col"][:8]) == [0, 1, 2, 3, 0, 1, 2, 3]          # the cycle
+    r = oracle.solve_lp(BEALE_A, BEALE_B, BEALE_C, ops, oracle.make_opts(rule=1))
+    assert r["status"] == 0 and r["n_pivots"] == 6 and r["fun"] == -1.25
+    r = oracle.solve_lp(BEALE_A, BEALE_B, BEALE_C, ops, oracle.make_opts(rule=0))      # automatic budget
+    assert r["status"] == 0 and abs(r["fun"] + 1.25) < 1e-9
+    np.testing.assert_allclose(r["x"], [1.0, 0.0, 1.0, 0.0], atol=1e-9)
