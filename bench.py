@@ -7,7 +7,8 @@ A "step" is one pass of the hot path over one batch of synthetic input: P pivots
   N = 1 : BASELINE config 4 -- one dense 16384 x 16384 fp64 tableau (2.1 GB > L2), Bland rule, fixed budget.
   N > 1 : BASELINE config 5 -- one dense 131072 x 131072 fp64 tableau (137 GB) column-sharded over the N GPUs,
           one all-gather of candidate columns per pivot (launched by torchrun, one rank per GPU).
-`value`   = pivots/s of the whole job with the tableau already resident in HBM (max over ranks, CUDA events).
+`value`   = pivot-update GB/s of the whole job (pivots/s x 2*R*C*8 bytes, all GPUs) with the tableau already resident
+            in HBM (max over ranks, CUDA events); `pivots_per_s` is printed beside it.
 `e2e`     = the same metric through the reference-facing C-ABI call with HOST buffers (b200lp_solve_dense from
             pinned host arrays A, b, c -> x, z), host<->device copies inside the timed region.
 `roofline`= pivot-update kernel: algorithmic bytes per launch (2*R*C*8) / its average duration, measured live with
@@ -32,6 +33,10 @@ sys.path.insert(0, ROOT)
 import numpy as np  # noqa: E402
 
 FALLBACK_HBM_GBS = 6650.0  # /opt/skills/guides/B200_PROFILING.md
+# BASELINE.json's metric is "pivots/sec and pivot-update HBM GB/s".  `value` is the GB/s form -- pivots/s x 2*R*C*8
+# bytes, summed over the GPUs -- because it is comparable between the 1-GPU tableau (config 4) and the sharded one
+# (config 5) that the 1/2/4/8-GPU series is made of; pivots/s is printed beside it as `pivots_per_s`.
+METRIC = "pivot_update_hbm_GBps"
 
 
 def measured_peak():
@@ -154,14 +159,16 @@ def run_reference_arm(args):
     pps = n / dt
     if args.gpus > 1:
         pps *= C / args.cols_total
+    bpp = 16.0 * args.rows * args.cols_total
+    gbps = pps * bpp / 1e9
     line = {
-        "impl": "reference", "metric": "pivots_per_s", "value": pps, "unit": "pivots/s", "n_gpus": args.gpus,
+        "impl": "reference", "metric": METRIC, "value": gbps, "unit": "GB/s", "pivots_per_s": pps, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True,
         "scaling": "strong" if args.gpus > 1 else "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": workload_config(args),
-        "cpu_baseline": {"value": pps, "unit": "pivots/s", "cores": threads, "kind": "port", "sample": note,
-                         "host_cpus": os.cpu_count()},
-        "e2e": {"value": pps, "unit": "pivots/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "cpu_baseline": {"value": gbps, "unit": "GB/s", "pivots_per_s": pps, "cores": threads, "kind": "port",
+                         "sample": note, "host_cpus": os.cpu_count()},
+        "e2e": {"value": gbps, "unit": "GB/s", "pivots_per_s": pps, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line))
@@ -282,7 +289,8 @@ def _bench_single_gpu(args):
     e1.record()
     torch.cuda.synchronize()
     e2e_sec = e0.elapsed_time(e1) * 1e-3
-    e2e = {"value": piv2 / e2e_sec, "unit": "pivots/s", "h2d_bytes_per_step": int(8 * (m * n + m + n)),
+    e2e = {"value": piv2 / e2e_sec * bytes_per_pivot / 1e9, "unit": "GB/s", "pivots_per_s": piv2 / e2e_sec,
+           "h2d_bytes_per_step": int(8 * (m * n + m + n)),
            "d2h_bytes_per_step": int(8 * (n + 1) + 128), "steps": e2e_steps, "ms_per_step": e2e_sec / e2e_steps * 1e3,
            "call": "b200lp_solve_dense(A, b, c, ops from pinned host memory) -> x, c'x on the host"}
     s2.close()
@@ -294,14 +302,15 @@ def _bench_single_gpu(args):
     if not args.no_cpu:
         cpu_piv = args.cpu_pivots
         pps, threads, dt = cpu_pivots_per_s(R, C, 1 if args.rule == "bland" else 0, cpu_piv, args.seed)
-        cpu = {"value": pps, "unit": "pivots/s", "cores": threads, "kind": "port", "host_cpus": os.cpu_count(),
+        cpu = {"value": pps * bytes_per_pivot / 1e9, "unit": "GB/s", "pivots_per_s": pps, "cores": threads, "kind": "port",
+               "host_cpus": os.cpu_count(),
                "sample": f"{cpu_piv} pivots of the same {R}x{C} tableau with oracle/ (OpenMP), {dt:.1f} s"}
 
     line = {
-        "metric": "pivots_per_s", "value": value, "unit": "pivots/s", "n_gpus": 1, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": sec / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": workload_config(args),
-        "hbm_GBps": value * bytes_per_pivot / 1e9, "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
+        "metric": METRIC, "value": value * bytes_per_pivot / 1e9, "unit": "GB/s", "pivots_per_s": value, "n_gpus": 1,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec / args.steps * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": workload_config(args),
+        "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
         "gpu_launches": int(launches), "clocks": clocks,
     }
     if args.secondary:
@@ -333,7 +342,9 @@ def secondary_configs(args):
     t0 = time.perf_counter()
     r = s.solve_dense(A, b, cmin, ops)
     gpu_s = time.perf_counter() - t0
-    c2 = {"gpu_e2e_s": gpu_s, "gpu_device_ms": r["device_ms"], "pivots": r["n_pivots"], "z": -r["fun"],
+    c2 = {"loop": "on-chip persistent kernel (tableau resident in shared memory, 1 grid barrier per pivot)",
+          "gpu_e2e_s": gpu_s, "gpu_device_ms": r["device_ms"], "pivots": r["n_pivots"], "z": -r["fun"],
+          "kernel_launches": r["kernel_launches"],
           "pivots_per_s": r["n_pivots"] / (r["device_ms"] * 1e-3), "us_per_pivot": r["device_ms"] * 1e3 / r["n_pivots"]}
     try:
         from scipy.optimize import linprog
@@ -347,15 +358,46 @@ def secondary_configs(args):
         c2["reference_highs_s"] = f"unavailable: {e}"
     out["config2_dense1024_dantzig"] = c2
     # config 3: 100k x (20 x 30) batched (one GPU's view: the whole batch)
+    import ctypes as C
     B = args.batch
     Ab, bb, cb, ob = W.batched_small_lps(0, B)
-    s.solve_batched(Ab[:1000], bb[:1000], cb[:1000], ob[:1000])
-    t0 = time.perf_counter()
-    rb = s.solve_batched(Ab, bb, cb, ob, want_x=True)
-    wall = time.perf_counter() - t0
-    c3 = {"batch": B, "kernel_ms": rb["device_ms"], "LPs_per_s_kernel": B / (rb["device_ms"] * 1e-3),
-          "LPs_per_s_e2e_pageable_host": B / wall, "pivots": int(rb["n_pivots"].sum()),
-          "pivots_per_s_kernel": float(rb["n_pivots"].sum()) / (rb["device_ms"] * 1e-3),
+    m3, n3 = Ab.shape[1], Ab.shape[2]
+    o = native.make_opts()
+    # (a) kernel alone: inputs and outputs resident in HBM
+    dev = [torch.from_numpy(a).cuda() for a in (Ab, bb, cb, ob)]
+    dout = [torch.empty(B, dtype=torch.int32, device="cuda"), torch.empty(B, dtype=torch.float64, device="cuda"),
+            torch.empty((B, n3), dtype=torch.float64, device="cuda"), torch.empty(B, dtype=torch.int32, device="cuda")]
+    torch.cuda.synchronize()
+    kernel_ms = min(s.solve_batched_device(B, m3, n3, dev[0].data_ptr(), dev[1].data_ptr(), dev[2].data_ptr(),
+                                           dev[3].data_ptr(), dout[0].data_ptr(), dout[1].data_ptr(), dout[2].data_ptr(),
+                                           dout[3].data_ptr(), o) for _ in range(3))
+    # (b) end to end from PINNED host buffers through the C ABI (H2D of A, b, c, ops and D2H of status, z, x, counts
+    #     inside the call, chunked over two streams so that copies overlap the kernels)
+    pin = [torch.from_numpy(a).pin_memory() for a in (Ab, bb, cb, ob)]
+    outs = [torch.empty(B, dtype=torch.int32).pin_memory(), torch.empty(B, dtype=torch.float64).pin_memory(),
+            torch.empty((B, n3), dtype=torch.float64).pin_memory(), torch.empty(B, dtype=torch.int32).pin_memory()]
+    ms = C.c_double()
+
+    def call():
+        native.check(native.lib().b200lp_solve_batched(
+            s._h, B, m3, n3, C.c_void_p(pin[0].data_ptr()), C.c_void_p(pin[1].data_ptr()),
+            C.c_void_p(pin[2].data_ptr()), C.c_void_p(pin[3].data_ptr()), C.byref(o), C.c_void_p(outs[0].data_ptr()),
+            C.c_void_p(outs[1].data_ptr()), C.c_void_p(outs[2].data_ptr()), C.c_void_p(outs[3].data_ptr()), None, 0, 0,
+            C.byref(ms)))
+    call()
+    walls = []
+    for _ in range(3):
+        t0 = time.perf_counter()
+        call()
+        walls.append(time.perf_counter() - t0)
+    wall_pinned = min(walls)
+    rb = {"status": outs[0].numpy(), "fun": outs[1].numpy(), "n_pivots": outs[3].numpy()}
+    assert (dout[0].cpu().numpy() == rb["status"]).all()
+    h2d = Ab.nbytes + bb.nbytes + cb.nbytes + ob.nbytes
+    c3 = {"batch": B, "kernel_ms": kernel_ms, "LPs_per_s_kernel": B / (kernel_ms * 1e-3),
+          "LPs_per_s_e2e_pinned_host": B / wall_pinned, "e2e_pinned_ms": wall_pinned * 1e3, "h2d_bytes": int(h2d),
+          "d2h_bytes": int(B * (4 + 8 + 8 * n3 + 4)), "pivots": int(rb["n_pivots"].sum()),
+          "pivots_per_s_kernel": float(rb["n_pivots"].sum()) / (kernel_ms * 1e-3),
           "status_counts": {int(k): int(v) for k, v in zip(*np.unique(rb["status"], return_counts=True))}}
     try:
         from scipy.optimize import linprog
@@ -475,17 +517,18 @@ def _bench_sharded(args, rank, local, world):
     torch.cuda.synchronize()
     t2 = torch.tensor([e0.elapsed_time(e1) * 1e-3], dtype=torch.float64, device=f"cuda:{local}")
     dist.all_reduce(t2, op=dist.ReduceOp.MAX)
-    e2e = {"value": nq / float(t2.item()), "unit": "pivots/s", "h2d_bytes_per_step": 0,
+    e2e = {"value": nq / float(t2.item()) * bytes_per_pivot / 1e9, "unit": "GB/s", "pivots_per_s": nq / float(t2.item()),
+           "h2d_bytes_per_step": 0,
            "d2h_bytes_per_step": int(8 * (n_total + 1)),
            "note": "inputs generated on the device inside the timed region: a 137 GB tableau cannot be staged "
                    "through host memory (SURVEY.md 8d); x*, z are read back to the host"}
     launches = args.steps * args.pivots * 5
     if rank == 0:
         line = {
-            "metric": "pivots_per_s", "value": value, "unit": "pivots/s", "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": sec / args.steps * 1e3, "higher_is_better": True,
-            "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": workload_config(args), "hbm_GBps": value * bytes_per_pivot / 1e9, "roofline": roofline,
+            "metric": METRIC, "value": value * bytes_per_pivot / 1e9, "unit": "GB/s", "pivots_per_s": value,
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec / args.steps * 1e3,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": workload_config(args), "roofline": roofline,
             "cpu_baseline": None, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
             "collective": {"op": "all_gather_into_tensor (NCCL)", "bytes_per_rank_per_pivot": 8 * (R + 2)},
         }

@@ -183,6 +183,8 @@ int b200lp_solve_batched(b200lp_solver *s, int64_t B, int64_t m, int64_t n, cons
                          const double *c, const int8_t *ops, const b200lp_opts *o, int32_t *status, double *fun,
                          double *x, int32_t *n_pivots, int32_t *piv_log, int64_t log_cap, int32_t on_device,
                          double *device_ms);
+/* device_ms: kernel time with device pointers; with host pointers the span from the first H2D to the last D2H (the
+ * batch is cut into 8 chunks on two streams so that copies overlap the kernels).                               */
 
 /* ---- measurement helpers ----------------------------------------------------------------------------- */
 /* time `reps` launches of the pivot-update kernel alone on pivot (row, col) of the attached tableau

@@ -13,6 +13,7 @@
 #include <algorithm>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -100,6 +101,7 @@ struct b200lp_solver {
     int sm_count = 148;
     cudaStream_t own_stream = nullptr;
     cudaStream_t stream = nullptr;
+    cudaStream_t stream2 = nullptr;  // second lane of the chunked host path of solve_batched
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_state[2] = {nullptr, nullptr};
 
     // tableau (attached: caller owned; otherwise `own_T`)
@@ -231,6 +233,7 @@ B200LP_API int b200lp_destroy(b200lp_solver* s) {
     cudaEventDestroy(s->ev_state[0]);
     cudaEventDestroy(s->ev_state[1]);
     if (s->own_stream) cudaStreamDestroy(s->own_stream);
+    if (s->stream2) cudaStreamDestroy(s->stream2);
     delete s;
     return 0;
 }
@@ -571,7 +574,9 @@ struct OnchipPlan {
 
 static bool onchip_plan(const b200lp_solver* s, OnchipPlan* plan) {
     if (s->C < 2 || s->snaps) return false;
-    const int64_t G = std::min<int64_t>(s->sm_count, s->C - 1);
+    int64_t gmax = s->sm_count;
+    if (const char* e = getenv("B200LP_ONCHIP_CTAS")) gmax = std::max<int64_t>(1, std::min<int64_t>(gmax, atoll(e)));  // tuning aid
+    const int64_t G = std::min<int64_t>(gmax, s->C - 1);
     const int64_t wmax = (s->C - 1 + G - 1) / G;
     int64_t stride = wmax + 1;
     if ((stride & 1) == 0) ++stride;
@@ -1165,6 +1170,7 @@ B200LP_API int b200lp_solve_batched(b200lp_solver* s, int64_t B, int64_t m, int6
     const int8_t* dops = ops;
     int32_t *dstatus = status, *dnp = n_pivots, *dlog = piv_log;
     double *dfun = fun, *dx = x;
+    const bool want_log = piv_log && log_cap > 0;
     if (!on_device) {
         CKR(s->sA.ensure((size_t)std::max<int64_t>(B * m * n, 1)));
         CKR(s->sb.ensure((size_t)std::max<int64_t>(B * m, 1)));
@@ -1174,13 +1180,7 @@ B200LP_API int b200lp_solve_batched(b200lp_solver* s, int64_t B, int64_t m, int6
         CKR(s->snpiv.ensure((size_t)B));
         CKR(s->sfun.ensure((size_t)B));
         if (x) CKR(s->sx.ensure((size_t)(B * n)));
-        if (piv_log && log_cap > 0) CKR(s->slog.ensure((size_t)(B * log_cap * 2)));
-        if (m > 0) {
-            CK(cudaMemcpyAsync(s->sA.p, A, (size_t)(B * m * n) * 8, cudaMemcpyHostToDevice, s->stream));
-            CK(cudaMemcpyAsync(s->sb.p, b, (size_t)(B * m) * 8, cudaMemcpyHostToDevice, s->stream));
-            CK(cudaMemcpyAsync(s->sops.p, ops, (size_t)(B * m), cudaMemcpyHostToDevice, s->stream));
-        }
-        CK(cudaMemcpyAsync(s->sc.p, c, (size_t)(B * n) * 8, cudaMemcpyHostToDevice, s->stream));
+        if (want_log) CKR(s->slog.ensure((size_t)(B * log_cap * 2)));
         dA = s->sA.p;
         db = s->sb.p;
         dc = s->sc.p;
@@ -1189,9 +1189,8 @@ B200LP_API int b200lp_solve_batched(b200lp_solver* s, int64_t B, int64_t m, int6
         dnp = s->snpiv.p;
         dfun = s->sfun.p;
         dx = x ? s->sx.p : nullptr;
-        dlog = (piv_log && log_cap > 0) ? s->slog.p : nullptr;
+        dlog = want_log ? s->slog.p : nullptr;
     }
-    P.B = B;
     P.m = (int32_t)m;
     P.n = (int32_t)n;
     P.ld = (int32_t)ld;
@@ -1202,29 +1201,57 @@ B200LP_API int b200lp_solve_batched(b200lp_solver* s, int64_t B, int64_t m, int6
     P.eps_cost = o->eps_cost;
     P.eps_pivot = o->eps_pivot;
     P.eps_feas = o->eps_feas;
-    P.A = dA;
-    P.b = db;
-    P.c = dc;
-    P.ops = dops;
-    P.status = dstatus;
-    P.fun = dfun;
-    P.x = dx;
-    P.n_pivots = dnp;
-    P.piv_log = dlog;
     P.warp_bytes = warp_bytes;
-    const int64_t blocks = (B + wpc - 1) / wpc;
-    CK(cudaEventRecord(s->ev0, s->stream));
-    k_solve_batched<<<(unsigned)blocks, wpc * 32, smem, s->stream>>>(P);
-    s->launches++;
-    CK(cudaGetLastError());
-    CK(cudaEventRecord(s->ev1, s->stream));
-    if (!on_device) {
-        CK(cudaMemcpyAsync(status, dstatus, (size_t)B * 4, cudaMemcpyDeviceToHost, s->stream));
-        CK(cudaMemcpyAsync(n_pivots, dnp, (size_t)B * 4, cudaMemcpyDeviceToHost, s->stream));
-        CK(cudaMemcpyAsync(fun, dfun, (size_t)B * 8, cudaMemcpyDeviceToHost, s->stream));
-        if (x) CK(cudaMemcpyAsync(x, dx, (size_t)(B * n) * 8, cudaMemcpyDeviceToHost, s->stream));
-        if (dlog) CK(cudaMemcpyAsync(piv_log, dlog, (size_t)(B * log_cap * 2) * 4, cudaMemcpyDeviceToHost, s->stream));
+
+    // Host inputs: the batch is cut into chunks that alternate between two streams, so that the H2D copy of one
+    // chunk overlaps the kernel of the previous one and the D2H of the one before (PCIe is the bound of this path).
+    const int nchunk = (!on_device && B >= 16384) ? 8 : 1;
+    cudaStream_t q[2] = {s->stream, s->stream};
+    if (nchunk > 1) {
+        if (!s->stream2) CK(cudaStreamCreateWithFlags(&s->stream2, cudaStreamNonBlocking));
+        q[1] = s->stream2;
     }
+    CK(cudaEventRecord(s->ev0, s->stream));
+    if (nchunk > 1) CK(cudaStreamWaitEvent(s->stream2, s->ev0, 0));
+    for (int k = 0; k < nchunk; ++k) {
+        const int64_t lo = B * k / nchunk, hi = B * (k + 1) / nchunk, nb = hi - lo;
+        if (nb <= 0) continue;
+        cudaStream_t st = q[k & 1];
+        if (!on_device) {
+            if (m > 0) {
+                CK(cudaMemcpyAsync(s->sA.p + lo * m * n, A + lo * m * n, (size_t)(nb * m * n) * 8, cudaMemcpyHostToDevice, st));
+                CK(cudaMemcpyAsync(s->sb.p + lo * m, b + lo * m, (size_t)(nb * m) * 8, cudaMemcpyHostToDevice, st));
+                CK(cudaMemcpyAsync(s->sops.p + lo * m, ops + lo * m, (size_t)(nb * m), cudaMemcpyHostToDevice, st));
+            }
+            CK(cudaMemcpyAsync(s->sc.p + lo * n, c + lo * n, (size_t)(nb * n) * 8, cudaMemcpyHostToDevice, st));
+        }
+        P.B = nb;
+        P.A = dA + lo * m * n;
+        P.b = db + lo * m;
+        P.c = dc + lo * n;
+        P.ops = dops + lo * m;
+        P.status = dstatus + lo;
+        P.fun = dfun + lo;
+        P.x = dx ? dx + lo * n : nullptr;
+        P.n_pivots = dnp + lo;
+        P.piv_log = dlog ? dlog + lo * log_cap * 2 : nullptr;
+        const int64_t blocks = (nb + wpc - 1) / wpc;
+        k_solve_batched<<<(unsigned)blocks, wpc * 32, smem, st>>>(P);
+        s->launches++;
+        CK(cudaGetLastError());
+        if (!on_device) {
+            CK(cudaMemcpyAsync(status + lo, dstatus + lo, (size_t)nb * 4, cudaMemcpyDeviceToHost, st));
+            CK(cudaMemcpyAsync(n_pivots + lo, dnp + lo, (size_t)nb * 4, cudaMemcpyDeviceToHost, st));
+            CK(cudaMemcpyAsync(fun + lo, dfun + lo, (size_t)nb * 8, cudaMemcpyDeviceToHost, st));
+            if (x) CK(cudaMemcpyAsync(x + lo * n, dx + lo * n, (size_t)(nb * n) * 8, cudaMemcpyDeviceToHost, st));
+            if (dlog) CK(cudaMemcpyAsync(piv_log + lo * log_cap * 2, dlog + lo * log_cap * 2, (size_t)(nb * log_cap * 2) * 4, cudaMemcpyDeviceToHost, st));
+        }
+    }
+    if (nchunk > 1) {
+        CK(cudaEventRecord(s->ev_state[0], s->stream2));
+        CK(cudaStreamWaitEvent(s->stream, s->ev_state[0], 0));
+    }
+    CK(cudaEventRecord(s->ev1, s->stream));
     CK(cudaStreamSynchronize(s->stream));
     if (device_ms) {
         float ms = 0.f;
