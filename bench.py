@@ -494,7 +494,8 @@ def _bench_sharded(args, rank, local, world):
     dist.all_reduce(tt, op=dist.ReduceOp.MAX)
     upd_ms = float(tt.item())
     achieved = shard_bytes / (upd_ms * 1e-3) / 1e9
-    roofline = {"bound": "hbm", "kernel": "k_update_ldg<256,8> (per shard)", "achieved": achieved, "peak": peak,
+    kname = "k_update_tma" if c_loc >= 32768 else "k_update_ldg<256,8>"   # b200lp.cu: resolve_variant (AUTO)
+    roofline = {"bound": "hbm", "kernel": kname + " (per shard)", "achieved": achieved, "peak": peak,
                 "unit": "GB/s", "frac": achieved / peak, "peak_source": peak_src, "traffic": None,
                 "algorithmic_bytes_per_launch": shard_bytes, "kernel_ms": {"update": upd_ms},
                 "loop_GBps_aggregate": value * bytes_per_pivot / 1e9,

@@ -179,3 +179,31 @@ def test_cuda_shard_engine_world1_and_emulated_world2(oracle, rule):
         for j, lab in enumerate(cl[:-1]):
             assert_bit_equal(T[:, j], one.T[:, pos[int(lab)]], f"shard {r} column of variable {lab}")
         assert_bit_equal(T[:, -1], one.T[:, -1], f"shard {r} rhs replica")
+
+
+def test_thirty_threads_share_the_library(golden):
+    """The reference's stress test drives one app from 30 threads (tests/test_performance_load.py:186-199): one
+    workspace per thread (native.thread_solver), ctypes releases the GIL, results must all be right."""
+    import threading
+    wrapper = golden["kat"]["K1_wyndor"]["problem"]
+    A, b, c, ops, mx = W.dense_feasible_lp(96, seed=1)
+    expect = native.thread_solver(0).solve_dense(A, b, -c, ops)
+    errors, results = [], []
+
+    def work(k):
+        try:
+            for _ in range(5):
+                rep = SolverController(wrapper).run()
+                z = rep["solucion_encontrada"]["valor_optimo_z"]
+                r = linprog(-c, A_ub=A, b_ub=b, bounds=[(0, None)] * 96)
+                results.append((abs(z - 36.0) < 1e-9, r.fun == expect["fun"], r.nit == expect["n_pivots"]))
+        except Exception as e:  # noqa: BLE001
+            errors.append(repr(e))
+
+    threads = [threading.Thread(target=work, args=(k,)) for k in range(30)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    assert not errors, errors[:3]
+    assert len(results) == 150 and all(all(r) for r in results)

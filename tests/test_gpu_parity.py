@@ -355,3 +355,34 @@ def test_beale_cycling_example_terminates_like_the_oracle(solver, oracle):
     gb = solver.solve_batched(A3, b3, c3, o3)
     assert (gb["status"] == 0).all() and (gb["n_pivots"] == ref["n_pivots"]).all()
     assert_bit_equal(gb["fun"], np.full(5, ref["fun"]), "batched fun")
+
+
+def test_config3_full_size_properties(solver):
+    """BASELINE config 3 at full size (100 000 LPs of 20 x 30, two-phase): size-independent properties.
+    Status pattern of the generator (index = 0 mod 100 infeasible, = 1 mod 100 unbounded, rest optimal), primal
+    feasibility and objective consistency of every optimal LP, non-negativity; checked for both rules."""
+    B = 100000
+    A, b, c, ops = W.batched_small_lps(0, B)
+    idx = np.arange(B)
+    funs = []
+    for rule in (native.RULE_DANTZIG, native.RULE_BLAND):
+        r = solver.solve_batched(A, b, c, ops, native.make_opts(rule=rule))
+        st = r["status"]
+        assert (st[idx % 100 == 0] == native.STATUS_INFEASIBLE).all()
+        assert (st[idx % 100 == 1] == native.STATUS_UNBOUNDED).all()
+        assert (st[idx % 100 > 1] == native.STATUS_OPTIMAL).all()
+        ok = st == 0
+        x = r["x"][ok]
+        assert (x >= -1e-9).all()
+        Ax = np.einsum("kij,kj->ki", A[ok], x)
+        tol = 1e-7 * np.maximum(1.0, np.abs(b[ok]))
+        o = ops[ok]
+        assert (Ax[o == 0] <= (b[ok] + tol)[o == 0]).all()
+        assert (Ax[o == 1] >= (b[ok] - tol)[o == 1]).all()
+        assert (np.abs(Ax - b[ok])[o == 2] <= tol[o == 2]).all()
+        cx = np.einsum("kj,kj->k", c[ok], x)
+        assert np.allclose(cx, r["fun"][ok], rtol=1e-9, atol=1e-9)
+        assert (r["n_pivots"][ok] > 0).all() and r["n_pivots"].max() < 400
+        funs.append(r["fun"][ok])
+    # both rules reach the same optimum
+    assert np.allclose(funs[0], funs[1], rtol=1e-9, atol=1e-9)
