@@ -750,7 +750,7 @@ B200LP_API int b200lp_run(b200lp_solver* s, const b200lp_opts* o, int64_t obj_ro
     const bool is_auto = o->max_pivots >= AUTO_BUDGET;
     const int64_t cap = is_auto ? auto_cap(s->m, s->C) : o->max_pivots;
     int64_t budget = cap;
-    CKR(ensure_hist(s, std::min<int64_t>(budget, r && r->hist_cap > 0 ? r->hist_cap : 16)));
+    CKR(ensure_hist(s, std::min<int64_t>(is_auto ? 2 * cap : cap, r && r->hist_cap > 0 ? r->hist_cap : 16)));
     CKR(launch_reset(s, budget, false));
     DevState fin;
     CK(cudaEventRecord(s->ev0, s->stream));
@@ -781,7 +781,7 @@ B200LP_API int b200lp_solve(b200lp_solver* s, const b200lp_opts* o, b200lp_resul
     const bool is_auto = o->max_pivots >= AUTO_BUDGET;
     const int64_t cap = is_auto ? auto_cap(s->m, s->C) : o->max_pivots;
     int64_t budget = cap;
-    CKR(ensure_hist(s, std::min<int64_t>(budget, r && r->hist_cap > 0 ? r->hist_cap : 16)));
+    CKR(ensure_hist(s, std::min<int64_t>(is_auto ? 2 * cap : cap, r && r->hist_cap > 0 ? r->hist_cap : 16)));
     CKR(launch_reset(s, budget, false));
     DevState fin;
     memset(&fin, 0, sizeof(fin));
@@ -1165,7 +1165,8 @@ B200LP_API int b200lp_solve_batched(b200lp_solver* s, int64_t B, int64_t m, int6
     // keep several CTAs per SM resident for latency hiding
     while (wpc > 1 && (size_t)wpc * warp_bytes > 48 * 1024) --wpc;
     const size_t smem = (size_t)wpc * warp_bytes;
-    CK(cudaFuncSetAttribute(k_solve_batched, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max));
+    CK(cudaFuncSetAttribute(k_solve_batched<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max));
+    CK(cudaFuncSetAttribute(k_solve_batched<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max));
 
     const double *dA = A, *db = b, *dc = c;
     const int8_t* dops = ops;
@@ -1237,7 +1238,8 @@ B200LP_API int b200lp_solve_batched(b200lp_solver* s, int64_t B, int64_t m, int6
         P.n_pivots = dnp + lo;
         P.piv_log = dlog ? dlog + lo * log_cap * 2 : nullptr;
         const int64_t blocks = (nb + wpc - 1) / wpc;
-        k_solve_batched<<<(unsigned)blocks, wpc * 32, smem, st>>>(P);
+        if (m + 2 >= 16) k_solve_batched<4><<<(unsigned)blocks, wpc * 32, smem, st>>>(P);
+        else k_solve_batched<1><<<(unsigned)blocks, wpc * 32, smem, st>>>(P);
         s->launches++;
         CK(cudaGetLastError());
         if (!on_device) {

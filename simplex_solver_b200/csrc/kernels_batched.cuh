@@ -44,6 +44,9 @@ struct WarpLP {
     int32_t m, n, R, C, ld, art_base;
 };
 
+// GROUP: rows whose loads are issued together before their stores (1 = plain loop, fewer registers: better for
+// short tableaux where occupancy matters more; 4 = measured best for the 22-row tableaux of config 3).
+template <int GROUP>
 __device__ __forceinline__ void wlp_pivot(const WarpLP& w, int r, int s, int lane) {
     for (int i = lane; i < w.R; i += 32) w.colbuf[i] = w.T[i * w.ld + s];
     __syncwarp();
@@ -52,11 +55,23 @@ __device__ __forceinline__ void wlp_pivot(const WarpLP& w, int r, int s, int lan
     for (int j = lane; j < w.C; j += 32) {
         const bool is_s = (j == s);
         const double q = is_s ? inv_p : w.T[r * w.ld + j] / p;
-        for (int i = 0; i < w.R; ++i) {
-            if (i == r) continue;
-            double* cell = w.T + i * w.ld + j;
-            const double t = is_s ? 0.0 : *cell;
-            *cell = __fma_rn(-w.colbuf[i], q, t);
+        // all loads of a group are issued before its stores, so the shared-memory latency of one row is hidden
+        // behind the others (a store cannot be reordered before an earlier load of unknown alias)
+        for (int i0 = 0; i0 < w.R; i0 += GROUP) {
+            double t[GROUP], cc[GROUP];
+#pragma unroll
+            for (int u = 0; u < GROUP; ++u) {
+                const int i = i0 + u;
+                if (i < w.R) {
+                    cc[u] = w.colbuf[i];
+                    t[u] = w.T[i * w.ld + j];
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < GROUP; ++u) {
+                const int i = i0 + u;
+                if (i < w.R && i != r) w.T[i * w.ld + j] = __fma_rn(-cc[u], q, is_s ? 0.0 : t[u]);
+            }
         }
         w.T[r * w.ld + j] = q;
     }
@@ -121,6 +136,7 @@ __device__ __forceinline__ void wlp_log(WarpRun& run, int r, int s, int lane) {
 }
 
 // one phase on objective row obj_row; returns a B200LP_STATUS_* code (0 = optimal for this row)
+template <int GROUP>
 __device__ __forceinline__ int wlp_run_phase(const WarpLP& w, int obj_row, int rule, double eps_cost, double eps_pivot,
                                              WarpRun& run, int lane) {
     for (;;) {
@@ -130,10 +146,11 @@ __device__ __forceinline__ int wlp_run_phase(const WarpLP& w, int obj_row, int r
         const int r = wlp_ratio(w, s, eps_pivot, lane);
         if (r < 0) return 3;
         wlp_log(run, r, s, lane);
-        wlp_pivot(w, r, s, lane);
+        wlp_pivot<GROUP>(w, r, s, lane);
     }
 }
 
+template <int GROUP>
 __device__ __forceinline__ int wlp_drive_out(const WarpLP& w, double eps_pivot, WarpRun& run, int lane) {
     for (int i = 0; i < w.m; ++i) {
         if (w.rowlab[i] < w.art_base) continue;
@@ -159,11 +176,12 @@ __device__ __forceinline__ int wlp_drive_out(const WarpLP& w, double eps_pivot, 
         }
         if (run.n_pivots >= run.max_pivots) return 1;
         wlp_log(run, i, k.pos, lane);
-        wlp_pivot(w, i, k.pos, lane);
+        wlp_pivot<GROUP>(w, i, k.pos, lane);
     }
     return 0;
 }
 
+template <int GROUP>
 __global__ void __launch_bounds__(256) k_solve_batched(const BatchedParams P) {
     extern __shared__ __align__(16) uint8_t smem_batched[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpc = blockDim.x >> 5;
@@ -267,22 +285,22 @@ __global__ void __launch_bounds__(256) k_solve_batched(const BatchedParams P) {
     const int cap = P.auto_budget ? 200 * (m + C) + 10000 : P.max_pivots;
     run.max_pivots = cap;
     if (n_obj == 2) {
-        st = wlp_run_phase(w, m + 1, rule, P.eps_cost, P.eps_pivot, run, lane);
+        st = wlp_run_phase<GROUP>(w, m + 1, rule, P.eps_cost, P.eps_pivot, run, lane);
         if (st == 1 && P.auto_budget && rule == 0) {  // Dantzig stalled: continue under Bland (cannot cycle)
             rule = 1;
             run.max_pivots += cap;
-            st = wlp_run_phase(w, m + 1, rule, P.eps_cost, P.eps_pivot, run, lane);
+            st = wlp_run_phase<GROUP>(w, m + 1, rule, P.eps_cost, P.eps_pivot, run, lane);
         }
         if (st == 3) st = 4;
         if (st == 0 && w.T[(m + 1) * ld + C - 1] < -P.eps_feas) st = 2;
-        if (st == 0) st = wlp_drive_out(w, P.eps_pivot, run, lane);
+        if (st == 0) st = wlp_drive_out<GROUP>(w, P.eps_pivot, run, lane);
     }
     if (st == 0) {
-        st = wlp_run_phase(w, m, rule, P.eps_cost, P.eps_pivot, run, lane);
+        st = wlp_run_phase<GROUP>(w, m, rule, P.eps_cost, P.eps_pivot, run, lane);
         if (st == 1 && P.auto_budget && rule == 0) {
             rule = 1;
             run.max_pivots += cap;
-            st = wlp_run_phase(w, m, rule, P.eps_cost, P.eps_pivot, run, lane);
+            st = wlp_run_phase<GROUP>(w, m, rule, P.eps_cost, P.eps_pivot, run, lane);
         }
     }
 
