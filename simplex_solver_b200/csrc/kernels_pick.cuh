@@ -10,6 +10,9 @@
 
 namespace b200lp {
 
+// Multi-CTA reductions finished by the last CTA to arrive.  (One fat CTA per kernel was measured slower at
+// 16384 x 16384: the strided column gather of the ratio test is limited by the loads ONE SM can keep in flight --
+// 40 us against 7 us with 64 CTAs.)  A single-CTA launch (small tableaux) skips partials, fence and ticket.
 constexpr int PICK_THREADS = 256;
 
 // Scale the row of the previous pivot (deferred so that the update kernel never writes row r while other
@@ -64,25 +67,27 @@ k_price(double* T, int64_t C, int64_t ld, int64_t obj_row, const int32_t* __rest
         }
     }
     k = block_key_min<BLAND>(k, sk);
-    if (threadIdx.x == 0) {
-        partials[blockIdx.x] = k;
+    if (gridDim.x > 1) {
+        if (threadIdx.x == 0) {
+            partials[blockIdx.x] = k;
+            __threadfence();
+            const unsigned int t = atomicAdd(&st->ticket_price, 1u);
+            is_last = (t == gridDim.x - 1);
+        }
+        __syncthreads();
+        if (!is_last) return;
         __threadfence();
-        const unsigned int t = atomicAdd(&st->ticket_price, 1u);
-        is_last = (t == gridDim.x - 1);
+        k = key_none();
+        for (int b = threadIdx.x; b < (int)gridDim.x; b += blockDim.x) {
+            Key c;
+            c.v = __ldcg(&partials[b].v);
+            c.lab = __ldcg(&partials[b].lab);
+            c.pos = __ldcg(&partials[b].pos);
+            k = key_min<BLAND>(k, c);
+        }
+        __syncthreads();
+        k = block_key_min<BLAND>(k, sk);
     }
-    __syncthreads();
-    if (!is_last) return;
-    __threadfence();
-    k = key_none();
-    for (int b = threadIdx.x; b < (int)gridDim.x; b += blockDim.x) {
-        Key c;
-        c.v = __ldcg(&partials[b].v);
-        c.lab = __ldcg(&partials[b].lab);
-        c.pos = __ldcg(&partials[b].pos);
-        k = key_min<BLAND>(k, c);
-    }
-    __syncthreads();
-    k = block_key_min<BLAND>(k, sk);
     if (threadIdx.x == 0) {
         st->ticket_price = 0;
         st->pend = 0;
@@ -190,27 +195,29 @@ k_ratio(const double* __restrict__ T, int64_t R, int64_t m, int64_t C, int64_t l
         }
     }
     k = block_key_min<false>(k, sk);
-    if (threadIdx.x == 0) {
-        partials[blockIdx.x] = k;
-        __threadfence();
-        const unsigned int t = atomicAdd(&st->ticket_ratio, 1u);
-        is_last = (t == gridDim.x - 1);
-    }
-    __syncthreads();
-    if (!is_last) return;
-    __threadfence();
-    k = key_none();
-    if (!ROW_PRESET) {
-        for (int b = threadIdx.x; b < (int)gridDim.x; b += blockDim.x) {
-            Key c;
-            c.v = __ldcg(&partials[b].v);
-            c.lab = __ldcg(&partials[b].lab);
-            c.pos = __ldcg(&partials[b].pos);
-            k = key_min<false>(k, c);
+    if (gridDim.x > 1) {
+        if (threadIdx.x == 0) {
+            partials[blockIdx.x] = k;
+            __threadfence();
+            const unsigned int t = atomicAdd(&st->ticket_ratio, 1u);
+            is_last = (t == gridDim.x - 1);
         }
+        __syncthreads();
+        if (!is_last) return;
+        __threadfence();
+        k = key_none();
+        if (!ROW_PRESET) {
+            for (int b = threadIdx.x; b < (int)gridDim.x; b += blockDim.x) {
+                Key c;
+                c.v = __ldcg(&partials[b].v);
+                c.lab = __ldcg(&partials[b].lab);
+                c.pos = __ldcg(&partials[b].pos);
+                k = key_min<false>(k, c);
+            }
+        }
+        __syncthreads();
+        k = block_key_min<false>(k, sk);
     }
-    __syncthreads();
-    k = block_key_min<false>(k, sk);
     if (threadIdx.x == 0) {
         st->ticket_ratio = 0;
         int r;
