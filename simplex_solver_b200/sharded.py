@@ -49,6 +49,22 @@ class CudaShardEngine:
     def reset(self, max_pivots):
         self.solver.shard_reset(max_pivots)
 
+    def capture_chunk(self, body):
+        """Capture `body` (library kernels + torch.distributed collectives) into a CUDA graph; None if capture fails."""
+        torch = self.torch
+        outer = torch.cuda.current_stream(self.device).cuda_stream
+        g = torch.cuda.CUDAGraph()
+        try:
+            torch.cuda.synchronize(self.device)
+            with torch.cuda.graph(g):
+                self.solver.set_stream(torch.cuda.current_stream(self.device).cuda_stream)
+                body()
+        except Exception:
+            g = None
+        finally:
+            self.solver.set_stream(outer)
+        return g
+
     def candidate(self, opts):
         self.solver.shard_candidate(opts, self.m, self.cand.data_ptr())
         return self.cand
@@ -78,6 +94,7 @@ class ShardedTableau:
     def __init__(self, engine, world: int = 1, rank: int = 0, group=None):
         self.engine, self.world, self.rank, self.group = engine, world, rank, group
         self.gathered = engine.new_buffer(world)
+        self._graphs = {}  # captured chunks, keyed by the options that are baked into the kernels' arguments
 
     @staticmethod
     def columns_of(n_total: int, world: int, rank: int):
@@ -91,16 +108,33 @@ class ShardedTableau:
         import torch.distributed as dist
         dist.all_gather_into_tensor(self.gathered, cand, group=self.group)
 
-    def run(self, opts, max_pivots: int, check_every: int = 0):
-        """Enqueue pivots until optimal / unbounded / max_pivots.  Returns (status, n_pivots)."""
+    def _chunk(self, opts, n):
+        eng = self.engine
+        for _ in range(n):
+            self._all_gather(eng.candidate(opts))
+            eng.pivot(opts, self.gathered, self.world, self.rank)
+
+    def run(self, opts, max_pivots: int, check_every: int = 0, use_graph: bool = True):
+        """Enqueue pivots until optimal / unbounded / max_pivots.  Returns (status, n_pivots).
+
+        On GPUs the per-pivot sequence (candidate kernels -> NCCL all-gather -> winner / ratio / update kernels) of a
+        whole chunk is captured once into a CUDA graph and replayed, so the host issues one launch per `check_every`
+        pivots instead of ~8 calls per pivot; the first chunk runs eagerly (it also warms NCCL up for capture).
+        """
         eng = self.engine
         eng.reset(max_pivots)
         check_every = check_every or max(1, min(max_pivots, 64))
+        key = (opts.rule, opts.update_variant, opts.eps_cost, opts.eps_pivot, check_every)
+        graph = self._graphs.get(key) if use_graph else None
         done_total = 0
         while True:
-            for _ in range(check_every):
-                self._all_gather(eng.candidate(opts))
-                eng.pivot(opts, self.gathered, self.world, self.rank)
+            if graph is not None:
+                graph.replay()
+            else:
+                self._chunk(opts, check_every)
+                if use_graph and hasattr(eng, "capture_chunk") and key not in self._graphs:
+                    self._graphs[key] = eng.capture_chunk(lambda: self._chunk(opts, check_every))
+                    graph = self._graphs[key]
             done_total += check_every
             done, status, n = eng.state()
             if done:
