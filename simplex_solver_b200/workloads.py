@@ -80,6 +80,37 @@ def batched_small_lps(start: int, count: int, m: int = 20, n: int = 30, base_see
     return A, b, c, ops
 
 
+def fuzz_lp(k: int, seed: int = 12345):
+    """k-th LP of a ragged stress family (shapes 1..12 x 1..12, mixed operators): rounded/degenerate coefficients
+    (k % 4 == 0), dense uniform (1), sparse (2), badly scaled rows 1e-3..1e3 (3); every 5th has a random right-hand
+    side (often infeasible); costs in [-1, 2) (often unbounded).  Returns (A, b, c_min, ops)."""
+    rng = np.random.default_rng([seed, k])
+    mm = int(rng.integers(1, 13))
+    nn = int(rng.integers(1, 13))
+    kind = k % 4
+    if kind == 0:
+        A = np.round(rng.uniform(-3, 3, (mm, nn)), 0)
+        x0 = np.round(rng.uniform(0, 2, nn), 0)
+    elif kind == 1:
+        A = rng.uniform(-1, 1, (mm, nn))
+        x0 = rng.uniform(0, 1, nn)
+    elif kind == 2:
+        A = rng.uniform(-2, 2, (mm, nn)) * (rng.random((mm, nn)) < 0.4)
+        x0 = rng.uniform(0, 1, nn)
+    else:
+        A = rng.uniform(-1, 1, (mm, nn)) * 10.0 ** rng.integers(-3, 4, (mm, 1))
+        x0 = rng.uniform(0, 1, nn)
+    ops = rng.integers(0, 3, mm).astype(np.int8)
+    slack = rng.uniform(0, 2, mm) * (rng.random(mm) < 0.7)
+    b = A @ x0 + np.where(ops == LE, slack, np.where(ops == GE, -slack, 0.0))
+    if k % 5 == 0:
+        b = rng.uniform(-3, 3, mm)
+    c = rng.uniform(-1, 2, nn)
+    if kind == 0:
+        c = np.round(c, 0)
+    return A + 0.0, b + 0.0, c + 0.0, ops
+
+
 def lp_to_problem_dict(A, b, c, ops, maximize: bool):
     """Array LP -> the reference's `problema_definicion` wrapper (ui_controller.py:63-67).
 

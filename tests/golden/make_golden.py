@@ -155,6 +155,15 @@ def main():
     golden["mixed"] = mixed
     print("mixed", Counter(r["status_text"] for r in mixed), Counter(r["scipy_status"] for r in mixed))
 
+    # a ragged stress family regenerated from (seed, k): degenerate, sparse and badly scaled LPs
+    fuzz = []
+    for k in range(1000):
+        Af, bf, cf, of = W.fuzz_lp(k)
+        g = run_reference(sc, W.lp_to_problem_dict(Af, bf, cf, of, False))
+        fuzz.append([g["scipy_status"], g["z"]])
+    golden["fuzz"] = {"seed": 12345, "count": 1000, "inputs_sha": sha(*W.fuzz_lp(7)), "results": fuzz}
+    print("fuzz", Counter(r[0] for r in fuzz))
+
     with open(os.path.join(HERE, "reference_golden.json"), "w") as f:
         json.dump(golden, f, indent=1)
     print("wrote reference_golden.json")

@@ -386,3 +386,46 @@ def test_config3_full_size_properties(solver):
         funs.append(r["fun"][ok])
     # both rules reach the same optimum
     assert np.allclose(funs[0], funs[1], rtol=1e-9, atol=1e-9)
+
+
+def test_fuzz_family_gpu_vs_oracle_and_reference(solver, oracle, golden):
+    """The ragged stress family through every single-LP path of the library (on-chip loop, graph loop with both update
+    kernels) and through the batched kernel: bit-identical to the oracle, status / z* as the reference path."""
+    g = golden["fuzz"]
+    modes = [dict(loop_mode=native.LOOP_AUTO), dict(loop_mode=native.LOOP_GRAPH, update_variant=native.UPDATE_LDG),
+             dict(loop_mode=native.LOOP_LAUNCHES, update_variant=native.UPDATE_TMA)]
+    for k in range(0, 400):
+        A, b, c, ops = W.fuzz_lp(k, g["seed"])
+        st, z = g["results"][k]
+        rule = k % 2
+        ref = oracle.solve_lp(A, b, c, ops, oracle.make_opts(rule=rule), hist_cap=512)
+        got = solver.solve_dense(A, b, c, ops, native.make_opts(rule=rule, **modes[k % 3]), hist_cap=512)
+        assert got["status"] == st == ref["status"], k
+        assert got["n_pivots"] == ref["n_pivots"] and got["n_phase1"] == ref["n_phase1"], k
+        np.testing.assert_array_equal(got["piv_row"], ref["piv_row"], err_msg=str(k))
+        np.testing.assert_array_equal(got["enter_lab"], ref["enter_lab"], err_msg=str(k))
+        if st == 0:
+            assert_bit_equal(got["fun"], ref["fun"], f"fuzz {k} fun")
+            assert_bit_equal(got["x"], ref["x"], f"fuzz {k} x")
+            assert abs(got["fun"] - z) <= REL * max(1.0, abs(z)), k
+    # batched kernel: group LPs of equal shape
+    shapes = {}
+    for k in range(g["count"]):
+        A, b, c, ops = W.fuzz_lp(k, g["seed"])
+        shapes.setdefault(A.shape, []).append((k, A, b, c, ops))
+    checked = 0
+    for shape, items in shapes.items():
+        if len(items) < 3:
+            continue
+        Ab = np.stack([it[1] for it in items])
+        bb = np.stack([it[2] for it in items])
+        cb = np.stack([it[3] for it in items])
+        ob = np.stack([it[4] for it in items])
+        got = solver.solve_batched(Ab, bb, cb, ob)
+        for i, it in enumerate(items):
+            st, z = g["results"][it[0]]
+            assert got["status"][i] == st, it[0]
+            if st == 0:
+                assert abs(got["fun"][i] - z) <= REL * max(1.0, abs(z)), it[0]
+            checked += 1
+    assert checked > 500

@@ -146,3 +146,24 @@ def test_beale_cycling_example_terminates(oracle):
     r = oracle.solve_lp(BEALE_A, BEALE_B, BEALE_C, ops, oracle.make_opts(rule=0))      # automatic budget
     assert r["status"] == 0 and abs(r["fun"] + 1.25) < 1e-9
     np.testing.assert_allclose(r["x"], [1.0, 0.0, 1.0, 0.0], atol=1e-9)
+
+
+def test_fuzz_family_against_reference(oracle, golden):
+    """1000 ragged LPs (degenerate, sparse, badly scaled; infeasible and unbounded ones included) solved by the
+    reference path: status identical, z* within 1e-9, for both entering rules."""
+    g = golden["fuzz"]
+    import hashlib
+    h = hashlib.sha256()
+    for a in W.fuzz_lp(7):
+        h.update(np.ascontiguousarray(a).tobytes())
+    assert h.hexdigest()[:16] == g["inputs_sha"]
+    seen = set()
+    for k, (st, z) in enumerate(g["results"]):
+        A, b, c, ops = W.fuzz_lp(k, g["seed"])
+        for rule in (0, 1):
+            r = oracle.solve_lp(A, b, c, ops, oracle.make_opts(rule=rule))
+            assert r["status"] == st, (k, rule)
+            if z is not None:
+                assert abs(r["fun"] - z) <= REL * max(1.0, abs(z)), (k, rule)
+        seen.add(st)
+    assert seen == {0, 2, 3}
