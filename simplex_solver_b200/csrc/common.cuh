@@ -59,17 +59,42 @@ __device__ __forceinline__ Key key_min(const Key& a, const Key& b) {
     return key_less_val(b, a) ? b : a;
 }
 
+// Order-preserving map double -> uint64 (for non-NaN x: a < b  <=>  ord(a) < ord(b)); -0.0 is folded into +0.0 first
+// so that the map agrees with operator< on zeros as well.
+__device__ __forceinline__ unsigned long long ord_f64(double x) {
+    const unsigned long long b = (unsigned long long)__double_as_longlong(x + 0.0);
+    return (b >> 63) ? ~b : (b | 0x8000000000000000ull);
+}
+
+// Warp-wide min of a Key under the same total orders as key_min<>, on the REDUX unit (__reduce_min_sync) instead of
+// five rounds of 4 shuffles + compares: value order = three 32-bit min-reductions (high word, low word, variable id),
+// label order = one.  Every lane returns the winning Key (key_none() if no lane has a candidate).
 template <bool BY_LABEL>
 __device__ __forceinline__ Key warp_key_min(Key k) {
-#pragma unroll
-    for (int off = 16; off > 0; off >>= 1) {
-        Key o;
-        o.v = __shfl_xor_sync(0xffffffffu, k.v, off);
-        o.lab = __shfl_xor_sync(0xffffffffu, k.lab, off);
-        o.pos = __shfl_xor_sync(0xffffffffu, k.pos, off);
-        k = key_min<BY_LABEL>(k, o);
+    const unsigned FULL = 0xffffffffu;
+    const bool has = k.lab != B200LP_NO_LAB;
+    bool win;
+    if (BY_LABEL) {
+        const unsigned ml = __reduce_min_sync(FULL, (unsigned)k.lab);  // NO_LAB is the largest id
+        if (ml == (unsigned)B200LP_NO_LAB) return key_none();
+        win = (unsigned)k.lab == ml;
+    } else {
+        if (!__any_sync(FULL, has)) return key_none();
+        const unsigned long long o = ord_f64(k.v);
+        const unsigned hi = (unsigned)(o >> 32), lo = (unsigned)o;
+        const unsigned mh = __reduce_min_sync(FULL, has ? hi : 0xffffffffu);
+        const bool in1 = has && hi == mh;
+        const unsigned mlo = __reduce_min_sync(FULL, in1 ? lo : 0xffffffffu);
+        const bool in2 = in1 && lo == mlo;
+        const unsigned ml = __reduce_min_sync(FULL, in2 ? (unsigned)k.lab : 0xffffffffu);
+        win = in2 && (unsigned)k.lab == ml;
     }
-    return k;
+    const int src = __ffs(__ballot_sync(FULL, win)) - 1;
+    Key r;
+    r.v = __shfl_sync(FULL, k.v, src);
+    r.lab = __shfl_sync(FULL, k.lab, src);
+    r.pos = __shfl_sync(FULL, k.pos, src);
+    return r;
 }
 
 // CTA-wide min of a Key; result valid in every thread of warp 0.  smem: one Key per warp.

@@ -55,23 +55,29 @@ __device__ __forceinline__ void wlp_pivot(const WarpLP& w, int r, int s, int lan
     for (int j = lane; j < w.C; j += 32) {
         const bool is_s = (j == s);
         const double q = is_s ? inv_p : w.T[r * w.ld + j] / p;
-        // all loads of a group are issued before its stores, so the shared-memory latency of one row is hidden
-        // behind the others (a store cannot be reordered before an earlier load of unknown alias)
-        for (int i0 = 0; i0 < w.R; i0 += GROUP) {
+        // The rank-1 update runs over ALL rows without per-element predicates -- row r gets a throw-away value and is
+        // overwritten with q right after.  All loads of a group are issued before its stores, so the shared-memory
+        // latency of one row hides behind the others (a store cannot move above an earlier load of unknown alias).
+        double* cell = w.T + j;
+        const double* cb = w.colbuf;
+        int i = 0;
+        for (; i + GROUP <= w.R; i += GROUP) {
             double t[GROUP], cc[GROUP];
 #pragma unroll
             for (int u = 0; u < GROUP; ++u) {
-                const int i = i0 + u;
-                if (i < w.R) {
-                    cc[u] = w.colbuf[i];
-                    t[u] = w.T[i * w.ld + j];
-                }
+                cc[u] = cb[u];
+                t[u] = cell[u * w.ld];
             }
 #pragma unroll
-            for (int u = 0; u < GROUP; ++u) {
-                const int i = i0 + u;
-                if (i < w.R && i != r) w.T[i * w.ld + j] = __fma_rn(-cc[u], q, is_s ? 0.0 : t[u]);
-            }
+            for (int u = 0; u < GROUP; ++u) cell[u * w.ld] = __fma_rn(-cc[u], q, is_s ? 0.0 : t[u]);
+            cell += GROUP * w.ld;
+            cb += GROUP;
+        }
+        for (; i < w.R; ++i) {
+            const double t = *cell;
+            *cell = __fma_rn(-cb[0], q, is_s ? 0.0 : t);
+            cell += w.ld;
+            ++cb;
         }
         w.T[r * w.ld + j] = q;
     }
