@@ -20,6 +20,7 @@
 
 #include "common.cuh"
 #include "kernels_batched.cuh"
+#include "kernels_blocked.cuh"
 #include "kernels_build.cuh"
 #include "kernels_onchip.cuh"
 #include "kernels_pick.cuh"
@@ -89,8 +90,9 @@ struct GraphKey {
     int64_t hist_cap = 0;
     const double* snaps = nullptr;
     int64_t snap_cap = 0;
+    int32_t blocked_k = 0;  // 0: rank-1 iterations; K > 0: look-ahead blocks of K pivots
     bool operator==(const GraphKey& o) const {
-        return snaps == o.snaps && snap_cap == o.snap_cap && T == o.T && R == o.R && C == o.C && ld == o.ld && obj_row == o.obj_row && rule == o.rule &&
+        return blocked_k == o.blocked_k && snaps == o.snaps && snap_cap == o.snap_cap && T == o.T && R == o.R && C == o.C && ld == o.ld && obj_row == o.obj_row && rule == o.rule &&
                variant == o.variant && iters == o.iters && eps_cost == o.eps_cost && eps_pivot == o.eps_pivot &&
                hist_cap == o.hist_cap;
     }
@@ -123,6 +125,11 @@ struct b200lp_solver {
     DevBuf<RowInfo> sinfo;
     DevBuf<int8_t> sops;
     DevBuf<int32_t> sstatus, snpiv, slog;
+
+    // look-ahead (blocked) loop: pending pivots' columns / rows and the current objective row / right-hand side
+    DevBuf<double> blk_colP, blk_qP, blk_obj, blk_rhs;
+    DevBuf<BlkPending> blk_pend;
+    BlkBuffers blk;
 
     // on-chip persistent loop: exchange buffer and grid-barrier counter
     DevBuf<double> xbuf;
@@ -227,6 +234,11 @@ B200LP_API int b200lp_destroy(b200lp_solver* s) {
     s->slog.release();
     s->xbuf.release();
     s->gbar.release();
+    s->blk_colP.release();
+    s->blk_qP.release();
+    s->blk_obj.release();
+    s->blk_rhs.release();
+    s->blk_pend.release();
     if (s->st_host) cudaFreeHost(s->st_host);
     cudaEventDestroy(s->ev0);
     cudaEventDestroy(s->ev1);
@@ -521,6 +533,67 @@ static int enqueue_driveout(b200lp_solver* s, const b200lp_opts* o) {
     return 0;
 }
 
+// ---- look-ahead (blocked) loop ---------------------------------------------------------------------------------
+static int blk_setup(b200lp_solver* s) {
+    const int64_t Rpad = (s->R + 15) / 16 * 16, Cpad = (s->C + 15) / 16 * 16 + 16;
+    CKR(s->blk_colP.ensure((size_t)BLK_KMAX * Rpad));
+    CKR(s->blk_qP.ensure((size_t)BLK_KMAX * Cpad));
+    CKR(s->blk_obj.ensure((size_t)Cpad));
+    CKR(s->blk_rhs.ensure((size_t)Rpad));
+    CKR(s->blk_pend.ensure(1));
+    s->blk.pend = s->blk_pend.p;
+    s->blk.colP = s->blk_colP.p;
+    s->blk.qP = s->blk_qP.p;
+    s->blk.objcur = s->blk_obj.p;
+    s->blk.rhscur = s->blk_rhs.p;
+    s->blk.Rpad = Rpad;
+    s->blk.Cpad = Cpad;
+    return 0;
+}
+
+static int blk_block_size(const b200lp_opts* o) {
+    return o->check_every > 0 ? (int)std::max(1, std::min(BLK_KMAX, o->check_every)) : 8;
+}
+
+// one look-ahead pivot: price on the current objective row, ratio on the replayed column, record row/obj/rhs
+static int enqueue_blk_pick(b200lp_solver* s, const b200lp_opts* o, int64_t obj_row) {
+    const int pb = clampi((s->C + PICK_THREADS * 4 - 1) / (PICK_THREADS * 4), 1, 2 * s->sm_count);
+    if (o->rule == B200LP_RULE_BLAND)
+        k_price<true, false><<<pb, PICK_THREADS, 0, s->stream>>>(s->blk.objcur, s->C, s->C, 0, s->collab.p, s->art_base, o->eps_cost, s->st.p, s->part_price.p);
+    else
+        k_price<false, false><<<pb, PICK_THREADS, 0, s->stream>>>(s->blk.objcur, s->C, s->C, 0, s->collab.p, s->art_base, o->eps_cost, s->st.p, s->part_price.p);
+    const int rb = clampi((s->R + BLK_THREADS - 1) / BLK_THREADS, 1, 2 * s->sm_count);
+    k_blk_ratio<<<rb, BLK_THREADS, 0, s->stream>>>(s->T, s->R, s->m, s->C, s->ld, s->rowlab.p, s->collab.p, o->eps_pivot, s->st.p,
+                                                 s->part_ratio.p, s->blk, s->h_row.p, s->h_col.p, s->h_enter.p, s->h_leave.p,
+                                                 s->hist_cap);
+    const int wb = clampi((std::max(s->R, s->C) + BLK_THREADS - 1) / BLK_THREADS, 1, 2 * s->sm_count);
+    k_blk_row<<<wb, BLK_THREADS, 0, s->stream>>>(s->T, s->R, s->C, s->ld, obj_row, s->st.p, s->blk);
+    s->launches += 3;
+    CK(cudaGetLastError());
+    return 0;
+}
+
+static int enqueue_blk_flush(b200lp_solver* s, int K) {
+    const int tiles_c = (int)((s->C + 511) / 512);
+    int64_t tr = s->R * tiles_c / ((int64_t)s->sm_count * 8);
+    tr = std::max<int64_t>(8, std::min<int64_t>(BLK_TILE_ROWS, tr / 8 * 8));
+    const int64_t n_tiles = (s->R + tr - 1) / tr * tiles_c;
+    const int grid = clampi(n_tiles, 1, (int64_t)s->sm_count * 16);
+    if (K <= 4) k_blk_flush<4><<<grid, 256, 0, s->stream>>>(s->T, s->R, s->C, s->ld, s->st.p, s->blk, (int)tr, tiles_c, n_tiles);
+    else if (K <= 8) k_blk_flush<8><<<grid, 256, 0, s->stream>>>(s->T, s->R, s->C, s->ld, s->st.p, s->blk, (int)tr, tiles_c, n_tiles);
+    else k_blk_flush<16><<<grid, 256, 0, s->stream>>>(s->T, s->R, s->C, s->ld, s->st.p, s->blk, (int)tr, tiles_c, n_tiles);
+    k_blk_clear<<<1, 1, 0, s->stream>>>(s->st.p, s->blk);
+    s->launches += 2;
+    CK(cudaGetLastError());
+    return 0;
+}
+
+static int enqueue_blk_block(b200lp_solver* s, const b200lp_opts* o, int64_t obj_row, int K) {
+    for (int k = 0; k < K; ++k) CKR(enqueue_blk_pick(s, o, obj_row));
+    CKR(enqueue_blk_flush(s, K));
+    return 0;
+}
+
 static int default_check_every(const b200lp_solver* s) {
     // enough work per replay to hide the host's status read; big tableaux need few pivots per replay
     const double bytes = 16.0 * (double)s->R * (double)s->C;
@@ -529,8 +602,9 @@ static int default_check_every(const b200lp_solver* s) {
     return 64;
 }
 
-static int get_graph(b200lp_solver* s, const b200lp_opts* o, int64_t obj_row, int iters) {
+static int get_graph(b200lp_solver* s, const b200lp_opts* o, int64_t obj_row, int iters, int blocked_k = 0) {
     GraphKey k;
+    k.blocked_k = blocked_k;
     k.T = s->T;
     k.R = s->R;
     k.C = s->C;
@@ -553,7 +627,8 @@ static int get_graph(b200lp_solver* s, const b200lp_opts* o, int64_t obj_row, in
     cudaGraph_t g = nullptr;
     CK(cudaStreamBeginCapture(s->stream, cudaStreamCaptureModeThreadLocal));
     int rc = 0;
-    for (int i = 0; i < iters && !rc; ++i) rc = enqueue_iteration(s, o, obj_row);
+    for (int i = 0; i < iters && !rc; ++i)
+        rc = blocked_k ? enqueue_blk_block(s, o, obj_row, blocked_k) : enqueue_iteration(s, o, obj_row);
     cudaError_t e = cudaStreamEndCapture(s->stream, &g);
     s->launches = before;  // capture launched nothing
     if (rc) {
@@ -632,11 +707,21 @@ static int run_loop(b200lp_solver* s, const b200lp_opts* o, int64_t obj_row, int
         OnchipPlan plan;
         if (onchip_plan(s, &plan)) return run_onchip(s, o, obj_row, plan, final_state);
     }
+    const int blocked_k = (mode == 0 && o->loop_mode == B200LP_LOOP_BLOCKED && !s->snaps) ? blk_block_size(o) : 0;
     int iters = o->check_every > 0 ? o->check_every : default_check_every(s);
     if (mode == 1) iters = std::min(iters, 8);
+    if (blocked_k) {
+        iters = 4;  // look-ahead blocks per replay
+        CKR(launch_flush(s));
+        CKR(blk_setup(s));
+        const int ib = clampi((std::max(s->R, s->C) + BLK_THREADS - 1) / BLK_THREADS, 1, 2 * s->sm_count);
+        k_blk_init<<<ib, BLK_THREADS, 0, s->stream>>>(s->T, s->R, s->C, s->ld, obj_row, s->st.p, s->blk);
+        s->launches++;
+        CK(cudaGetLastError());
+    }
     const bool use_graph = o->loop_mode != B200LP_LOOP_LAUNCHES && mode == 0 && s->stream != (cudaStream_t)0;
-    if (use_graph) CKR(get_graph(s, o, obj_row, iters));
-    const int per_iter = s->snaps ? 4 : 3;
+    if (use_graph) CKR(get_graph(s, o, obj_row, iters, blocked_k));
+    const int per_iter = blocked_k ? 3 * blocked_k + 2 : (s->snaps ? 4 : 3);
     int slot = 0;
     bool first = true;
     for (;;) {
@@ -645,7 +730,8 @@ static int run_loop(b200lp_solver* s, const b200lp_opts* o, int64_t obj_row, int
             s->launches += (int64_t)per_iter * iters;
         } else {
             for (int i = 0; i < iters; ++i) {
-                if (mode == 0) CKR(enqueue_iteration(s, o, obj_row));
+                if (blocked_k) CKR(enqueue_blk_block(s, o, obj_row, blocked_k));
+                else if (mode == 0) CKR(enqueue_iteration(s, o, obj_row));
                 else CKR(enqueue_driveout(s, o));
             }
         }
@@ -736,7 +822,7 @@ static int check_opts(const b200lp_opts* o) {
     if (o->rule != B200LP_RULE_DANTZIG && o->rule != B200LP_RULE_BLAND) return fail(B200LP_E_INVALID, "unknown rule %d", o->rule);
     if (o->update_variant < 0 || o->update_variant > 2) return fail(B200LP_E_INVALID, "unknown update variant %d", o->update_variant);
     if (o->max_pivots < 0) return fail(B200LP_E_INVALID, "max_pivots < 0");
-    if (o->loop_mode < 0 || o->loop_mode > 2) return fail(B200LP_E_INVALID, "unknown loop_mode %d", o->loop_mode);
+    if (o->loop_mode < 0 || o->loop_mode > 3) return fail(B200LP_E_INVALID, "unknown loop_mode %d", o->loop_mode);
     return 0;
 }
 

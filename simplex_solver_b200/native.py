@@ -20,7 +20,7 @@ RULE_DANTZIG, RULE_BLAND = 0, 1
 STATUS_OPTIMAL, STATUS_LIMIT, STATUS_INFEASIBLE, STATUS_UNBOUNDED, STATUS_NUMERICAL = 0, 1, 2, 3, 4
 OP_LE, OP_GE, OP_EQ = 0, 1, 2
 UPDATE_AUTO, UPDATE_LDG, UPDATE_TMA = 0, 1, 2
-LOOP_LAUNCHES, LOOP_GRAPH, LOOP_AUTO = 0, 1, 2
+LOOP_LAUNCHES, LOOP_GRAPH, LOOP_AUTO, LOOP_BLOCKED = 0, 1, 2, 3
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",

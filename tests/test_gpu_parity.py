@@ -108,7 +108,7 @@ def test_dense_update_variants_agree(solver, oracle):
     cmin = to_min_form(c, mx)
     ref = oracle.solve_lp(A, b, cmin, ops, hist_cap=1 << 13)
     for variant in (native.UPDATE_LDG, native.UPDATE_TMA):
-        for mode in (native.LOOP_LAUNCHES, native.LOOP_GRAPH, native.LOOP_AUTO):
+        for mode in (native.LOOP_LAUNCHES, native.LOOP_GRAPH, native.LOOP_AUTO, native.LOOP_BLOCKED):
             got = solver.solve_dense(A, b, cmin, ops, native.make_opts(update_variant=variant, loop_mode=mode,
                                                                      check_every=16), hist_cap=1 << 13)
             assert got["n_pivots"] == ref["n_pivots"], (variant, mode)
@@ -150,7 +150,7 @@ def test_generated_tableau_and_single_phases_bit_exact(solver, oracle, shape):
         np.testing.assert_array_equal(cl, ot.collab)
 
 
-@pytest.mark.parametrize("variant", [native.UPDATE_LDG, native.UPDATE_TMA, "onchip"])
+@pytest.mark.parametrize("variant", [native.UPDATE_LDG, native.UPDATE_TMA, "onchip", "blocked3", "blocked8", "blocked16"])
 @pytest.mark.parametrize("rule", [native.RULE_BLAND, native.RULE_DANTZIG])
 def test_device_loop_fixed_budget_bit_exact(solver, oracle, rule, variant):
     """Config 4 in miniature: a fixed pivot budget on a generated square tableau, Bland and Dantzig, through the
@@ -160,6 +160,8 @@ def test_device_loop_fixed_budget_bit_exact(solver, oracle, rule, variant):
     solver.generate(4, n, 0)
     if variant == "onchip":
         o = native.make_opts(rule=rule, max_pivots=budget, loop_mode=native.LOOP_AUTO)
+    elif isinstance(variant, str):  # look-ahead blocks of K pivots (150 is not a multiple of 8 or 16: ragged last block)
+        o = native.make_opts(rule=rule, max_pivots=budget, loop_mode=native.LOOP_BLOCKED, check_every=int(variant[7:]))
     else:
         o = native.make_opts(rule=rule, max_pivots=budget, update_variant=variant, loop_mode=native.LOOP_GRAPH)
     got = solver.run(o, hist_cap=budget)
@@ -393,13 +395,14 @@ def test_fuzz_family_gpu_vs_oracle_and_reference(solver, oracle, golden):
     kernels) and through the batched kernel: bit-identical to the oracle, status / z* as the reference path."""
     g = golden["fuzz"]
     modes = [dict(loop_mode=native.LOOP_AUTO), dict(loop_mode=native.LOOP_GRAPH, update_variant=native.UPDATE_LDG),
-             dict(loop_mode=native.LOOP_LAUNCHES, update_variant=native.UPDATE_TMA)]
+             dict(loop_mode=native.LOOP_LAUNCHES, update_variant=native.UPDATE_TMA),
+             dict(loop_mode=native.LOOP_BLOCKED, check_every=5)]
     for k in range(0, 400):
         A, b, c, ops = W.fuzz_lp(k, g["seed"])
         st, z = g["results"][k]
         rule = k % 2
         ref = oracle.solve_lp(A, b, c, ops, oracle.make_opts(rule=rule), hist_cap=512)
-        got = solver.solve_dense(A, b, c, ops, native.make_opts(rule=rule, **modes[k % 3]), hist_cap=512)
+        got = solver.solve_dense(A, b, c, ops, native.make_opts(rule=rule, **modes[k % 4]), hist_cap=512)
         assert got["status"] == st == ref["status"], k
         assert got["n_pivots"] == ref["n_pivots"] and got["n_phase1"] == ref["n_phase1"], k
         np.testing.assert_array_equal(got["piv_row"], ref["piv_row"], err_msg=str(k))
