@@ -258,6 +258,27 @@ def _bench_single_gpu(args):
                 "loop_GBps": value * bytes_per_pivot / 1e9, "loop_frac_of_peak": value * bytes_per_pivot / 1e9 / peak,
                 "loop_frac_of_nominal_8TBs": value * bytes_per_pivot / 1e9 / 8000.0}
 
+    # ---- beyond the rank-1 roofline: look-ahead pivoting (same pivots, same tableau bits, 1 tableau pass per K) ----
+    lookahead = None
+    if args.lookahead:
+        lookahead = {}
+        for K in (8, 16, 32):
+            s.generate(args.seed, n, 0)
+            ob = native.make_opts(rule=rule, max_pivots=args.pivots * 4, loop_mode=native.LOOP_BLOCKED, check_every=K)
+            s.run(ob)
+            torch.cuda.synchronize()
+            b0, b1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            b0.record()
+            rb = s.run(ob)
+            b1.record()
+            torch.cuda.synchronize()
+            pps = rb["n_pivots"] / (b0.elapsed_time(b1) * 1e-3)
+            lookahead[f"K={K}"] = {"pivots_per_s": pps, "speedup_vs_rank1_loop": pps / value,
+                                   "hbm_bytes_per_pivot": bytes_per_pivot / K, "kernel_launches": rb["kernel_launches"]}
+        lookahead["note"] = ("loop_mode=BLOCKED: K pivots are decided from O(R+C) state and applied in one pass over the "
+                             "tableau; pivot sequence and tableau are bit-identical to the rank-1 loop (tests), HBM traffic "
+                             "per pivot is 2*R*C*8/K, so pivots/s is no longer bounded by the rank-1 roofline")
+
     # ---- e2e: the reference-facing call with HOST buffers (pinned), copies inside the timed region ----
     s.generate(args.seed, n, 0)
     torch.cuda.synchronize()
@@ -313,6 +334,8 @@ def _bench_single_gpu(args):
         "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
         "gpu_launches": int(launches), "clocks": clocks,
     }
+    if lookahead:
+        line["lookahead"] = lookahead
     if args.secondary:
         line["secondary"] = secondary_configs(args)
     print(json.dumps(line))
@@ -553,6 +576,7 @@ def main():
     ap.add_argument("--cpu-pivots", type=int, default=48, help="pivots of the cpu_baseline sample")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-secondary", dest="secondary", action="store_false")
+    ap.add_argument("--no-lookahead", dest="lookahead", action="store_false")
     args = ap.parse_args()
     world = int(os.environ.get("WORLD_SIZE", "1"))
     if world > 1:

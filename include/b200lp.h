@@ -66,7 +66,7 @@ extern "C" {
                                /* persistent cooperative kernel, SM-sharded and shared-memory resident, with  */
                                /* one grid barrier per pivot; larger ones use the graph                       */
 
-#define B200LP_LOOP_BLOCKED 3  /* look-ahead pivoting: K pivots (check_every, 1..16, default 8) are decided from    */
+#define B200LP_LOOP_BLOCKED 3  /* look-ahead pivoting: K pivots (check_every, 1..32, default 8) are decided from    */
                                /* O(R + C) state and applied to the tableau in ONE pass -- 2*R*C*8/K bytes of HBM  */
                                /* traffic per pivot, bit-identical pivots and tableau (kernels_blocked.cuh)        */
 

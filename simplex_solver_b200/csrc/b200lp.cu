@@ -555,33 +555,36 @@ static int blk_block_size(const b200lp_opts* o) {
     return o->check_every > 0 ? (int)std::max(1, std::min(BLK_KMAX, o->check_every)) : 8;
 }
 
-// one look-ahead pivot: price on the current objective row, ratio on the replayed column, record row/obj/rhs
+// one look-ahead pivot = two launches: [row part of the previous pivot + pricing] and [ratio on the replayed column]
 static int enqueue_blk_pick(b200lp_solver* s, const b200lp_opts* o, int64_t obj_row) {
-    const int pb = clampi((s->C + PICK_THREADS * 4 - 1) / (PICK_THREADS * 4), 1, 2 * s->sm_count);
+    const int wb = clampi((std::max(s->R, s->C) + BLK_THREADS * 2 - 1) / (BLK_THREADS * 2), 1, 2 * s->sm_count);
     if (o->rule == B200LP_RULE_BLAND)
-        k_price<true, false><<<pb, PICK_THREADS, 0, s->stream>>>(s->blk.objcur, s->C, s->C, 0, s->collab.p, s->art_base, o->eps_cost, s->st.p, s->part_price.p);
+        k_blk_rowprice<true><<<wb, BLK_THREADS, 0, s->stream>>>(s->T, s->R, s->C, s->ld, obj_row, s->collab.p, s->art_base,
+                                                               o->eps_cost, s->st.p, s->part_price.p, s->blk);
     else
-        k_price<false, false><<<pb, PICK_THREADS, 0, s->stream>>>(s->blk.objcur, s->C, s->C, 0, s->collab.p, s->art_base, o->eps_cost, s->st.p, s->part_price.p);
+        k_blk_rowprice<false><<<wb, BLK_THREADS, 0, s->stream>>>(s->T, s->R, s->C, s->ld, obj_row, s->collab.p, s->art_base,
+                                                                o->eps_cost, s->st.p, s->part_price.p, s->blk);
     const int rb = clampi((s->R + BLK_THREADS - 1) / BLK_THREADS, 1, 2 * s->sm_count);
     k_blk_ratio<<<rb, BLK_THREADS, 0, s->stream>>>(s->T, s->R, s->m, s->C, s->ld, s->rowlab.p, s->collab.p, o->eps_pivot, s->st.p,
                                                  s->part_ratio.p, s->blk, s->h_row.p, s->h_col.p, s->h_enter.p, s->h_leave.p,
                                                  s->hist_cap);
-    const int wb = clampi((std::max(s->R, s->C) + BLK_THREADS - 1) / BLK_THREADS, 1, 2 * s->sm_count);
-    k_blk_row<<<wb, BLK_THREADS, 0, s->stream>>>(s->T, s->R, s->C, s->ld, obj_row, s->st.p, s->blk);
-    s->launches += 3;
+    s->launches += 2;
     CK(cudaGetLastError());
     return 0;
 }
 
-static int enqueue_blk_flush(b200lp_solver* s, int K) {
+static int enqueue_blk_flush(b200lp_solver* s, int K, int64_t obj_row) {
+    // the row part of the block's last pivot (the fused kernel would only do it at the next pick)
+    const int wb = clampi((std::max(s->R, s->C) + BLK_THREADS - 1) / BLK_THREADS, 1, 2 * s->sm_count);
+    k_blk_row<<<wb, BLK_THREADS, 0, s->stream>>>(s->T, s->R, s->C, s->ld, obj_row, s->st.p, s->blk);
+    s->launches++;
     const int tiles_c = (int)((s->C + 511) / 512);
     int64_t tr = s->R * tiles_c / ((int64_t)s->sm_count * 8);
     tr = std::max<int64_t>(8, std::min<int64_t>(BLK_TILE_ROWS, tr / 8 * 8));
     const int64_t n_tiles = (s->R + tr - 1) / tr * tiles_c;
     const int grid = clampi(n_tiles, 1, (int64_t)s->sm_count * 16);
-    if (K <= 4) k_blk_flush<4><<<grid, 256, 0, s->stream>>>(s->T, s->R, s->C, s->ld, s->st.p, s->blk, (int)tr, tiles_c, n_tiles);
-    else if (K <= 8) k_blk_flush<8><<<grid, 256, 0, s->stream>>>(s->T, s->R, s->C, s->ld, s->st.p, s->blk, (int)tr, tiles_c, n_tiles);
-    else k_blk_flush<16><<<grid, 256, 0, s->stream>>>(s->T, s->R, s->C, s->ld, s->st.p, s->blk, (int)tr, tiles_c, n_tiles);
+    (void)K;
+    k_blk_flush<<<grid, 256, 0, s->stream>>>(s->T, s->R, s->C, s->ld, s->st.p, s->blk, (int)tr, tiles_c, n_tiles);
     k_blk_clear<<<1, 1, 0, s->stream>>>(s->st.p, s->blk);
     s->launches += 2;
     CK(cudaGetLastError());
@@ -590,7 +593,7 @@ static int enqueue_blk_flush(b200lp_solver* s, int K) {
 
 static int enqueue_blk_block(b200lp_solver* s, const b200lp_opts* o, int64_t obj_row, int K) {
     for (int k = 0; k < K; ++k) CKR(enqueue_blk_pick(s, o, obj_row));
-    CKR(enqueue_blk_flush(s, K));
+    CKR(enqueue_blk_flush(s, K, obj_row));
     return 0;
 }
 
@@ -721,7 +724,7 @@ static int run_loop(b200lp_solver* s, const b200lp_opts* o, int64_t obj_row, int
     }
     const bool use_graph = o->loop_mode != B200LP_LOOP_LAUNCHES && mode == 0 && s->stream != (cudaStream_t)0;
     if (use_graph) CKR(get_graph(s, o, obj_row, iters, blocked_k));
-    const int per_iter = blocked_k ? 3 * blocked_k + 2 : (s->snaps ? 4 : 3);
+    const int per_iter = blocked_k ? 2 * blocked_k + 3 : (s->snaps ? 4 : 3);
     int slot = 0;
     bool first = true;
     for (;;) {

@@ -20,7 +20,7 @@
 
 namespace b200lp {
 
-constexpr int BLK_KMAX = 16;
+constexpr int BLK_KMAX = 32;
 constexpr int BLK_THREADS = 256;
 
 // The number of pending (decided, unapplied) pivots is implicit: DevState.n_pivots - base.
@@ -184,20 +184,130 @@ k_blk_row(const double* __restrict__ T, int64_t R, int64_t C, int64_t ld, int64_
         B.rhscur[i] = (i == r) ? q_rhs : __fma_rn(-colT[i], q_rhs, B.rhscur[i]);
 }
 
+// Fused "row part of the previous look-ahead pivot" + "pricing of the next one": the thread that refreshes objcur[j]
+// prices it at once, so a look-ahead pivot costs two launches (this one and k_blk_ratio) instead of three.
+// DevState.have_pivot == 1 on entry means k_blk_ratio recorded a pivot whose row part is still due.
+template <bool BLAND>
+__global__ void __launch_bounds__(BLK_THREADS)
+k_blk_rowprice(const double* __restrict__ T, int64_t R, int64_t C, int64_t ld, int64_t obj_row,
+               const int32_t* __restrict__ collab, int32_t art_base, double eps_cost, DevState* st, Key* partials,
+               BlkBuffers B) {
+    __shared__ Key sk[BLK_THREADS / 32];
+    __shared__ bool is_last;
+    __shared__ int32_t sr[BLK_KMAX], ss[BLK_KMAX];
+    __shared__ double sinv[BLK_KMAX], sc[BLK_KMAX];
+    if (st->done) return;
+    const bool row_due = st->have_pivot != 0;
+    const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, nthr = (int64_t)gridDim.x * blockDim.x;
+    Key k = key_none();
+    if (row_due) {
+        const int t = (int)(st->n_pivots - 1 - B.pend->base);
+        const int r = st->r, s = st->s;
+        const double p = st->p, inv_p = st->inv_p;
+        if (threadIdx.x < t) {
+            sr[threadIdx.x] = B.pend->r[threadIdx.x];
+            ss[threadIdx.x] = B.pend->s[threadIdx.x];
+            sinv[threadIdx.x] = B.pend->inv_p[threadIdx.x];
+            sc[threadIdx.x] = B.colP[(int64_t)threadIdx.x * B.Rpad + r];
+        }
+        __syncthreads();
+        const double* colT = B.colP + (int64_t)t * B.Rpad;
+        double* qT = B.qP + (int64_t)t * B.Cpad;
+        const double c_obj = colT[obj_row];
+        const double q_rhs = B.pend->q_rhs;
+        for (int64_t j = tid; j < C; j += nthr) {
+            double v = T[(int64_t)r * ld + j];
+            for (int u = 0; u < t; ++u)
+                v = blk_step(v, r == sr[u], j == ss[u], sc[u], B.qP[(int64_t)u * B.Cpad + j], sinv[u]);
+            const double q = (j == s) ? inv_p : v / p;
+            qT[j] = q;
+            const double d = blk_step(B.objcur[j], false, j == s, c_obj, q, inv_p);
+            B.objcur[j] = d;
+            if (j < C - 1) {
+                // labels were swapped by k_blk_ratio already: collab[s] is the variable that just left the basis
+                const int32_t lab = collab[j];
+                if (lab < art_base && d < -eps_cost) {
+                    Key c;
+                    c.v = d;
+                    c.lab = lab;
+                    c.pos = (int32_t)j;
+                    k = key_min<BLAND>(k, c);
+                }
+            }
+        }
+        for (int64_t i = tid; i < R; i += nthr)
+            B.rhscur[i] = (i == r) ? q_rhs : __fma_rn(-colT[i], q_rhs, B.rhscur[i]);
+    } else {
+        for (int64_t j = tid; j < C - 1; j += nthr) {
+            const int32_t lab = collab[j];
+            const double d = B.objcur[j];
+            if (lab < art_base && d < -eps_cost) {
+                Key c;
+                c.v = d;
+                c.lab = lab;
+                c.pos = (int32_t)j;
+                k = key_min<BLAND>(k, c);
+            }
+        }
+    }
+    k = block_key_min<BLAND>(k, sk);
+    if (gridDim.x > 1) {
+        if (threadIdx.x == 0) {
+            partials[blockIdx.x] = k;
+            __threadfence();
+            const unsigned int tk = atomicAdd(&st->ticket_price, 1u);
+            is_last = (tk == gridDim.x - 1);
+        }
+        __syncthreads();
+        if (!is_last) return;
+        __threadfence();
+        k = key_none();
+        for (int b = threadIdx.x; b < (int)gridDim.x; b += blockDim.x) {
+            Key c;
+            c.v = __ldcg(&partials[b].v);
+            c.lab = __ldcg(&partials[b].lab);
+            c.pos = __ldcg(&partials[b].pos);
+            k = key_min<BLAND>(k, c);
+        }
+        __syncthreads();
+        k = block_key_min<BLAND>(k, sk);
+    }
+    if (threadIdx.x == 0) {
+        st->ticket_price = 0;
+        if (st->n_pivots >= st->max_pivots) {
+            st->done = 1;
+            st->status = 1;  // LIMIT
+            st->have_pivot = 0;
+        } else if (k.lab == B200LP_NO_LAB) {
+            st->done = 1;
+            st->status = 0;  // OPTIMAL for this objective row
+            st->have_pivot = 0;
+            st->s = -1;
+            st->enter_lab = -1;
+        } else {
+            st->have_pivot = 1;
+            st->s = k.pos;
+            st->enter_lab = k.lab;
+            st->best_val = k.v;
+        }
+    }
+}
+
 // The flush: every element of the stored tableau replays the pending steps in registers.  Same tiling as
-// k_update_ldg (256 threads x 2 columns x up to 64 rows, streaming 128-bit loads/stores, 8 rows in flight per thread);
-// q_u for the thread's two columns lives in registers for all pending u; the tile's slice of every col_u is staged in
-// shared memory once per tile and read as a broadcast.
+// k_update_ldg (256 threads x 2 columns x up to 64 rows, streaming 128-bit loads/stores, 8 rows in flight per thread).
+// The steps are taken in chunks of 8: q_u of the chunk for the thread's two columns is (re)loaded into registers per
+// row group (an L1/L2 hit), so the register footprint -- and with it the occupancy that hides the HBM latency -- does
+// not grow with K.  The tile's slice of every col_u is staged in shared memory once per tile (broadcast reads).
 constexpr int BLK_TILE_ROWS = 64;
 constexpr int BLK_UNROLL = 8;
+constexpr int BLK_CHUNK = 8;
 
-template <int KMAX>
-__global__ void __launch_bounds__(256, (KMAX <= 8 ? 2 : 1))
+__global__ void __launch_bounds__(256, 2)
 k_blk_flush(double* __restrict__ T, int64_t R, int64_t C, int64_t ld, const DevState* st, BlkBuffers B, int tile_rows,
             int tiles_c, int64_t n_tiles) {
     __shared__ int32_t sr[BLK_KMAX], ss[BLK_KMAX];
     __shared__ double sinv[BLK_KMAX];
-    __shared__ double scol[KMAX][BLK_TILE_ROWS];
+    __shared__ double scol[BLK_KMAX][BLK_TILE_ROWS];
     const int t = (int)(st->n_pivots - B.pend->base);
     if (t == 0) return;
     if (threadIdx.x < t) {
@@ -217,51 +327,51 @@ k_blk_flush(double* __restrict__ T, int64_t R, int64_t C, int64_t ld, const DevS
         __syncthreads();
         const int64_t j = tc * 512 + 2 * threadIdx.x;
         if (j >= C) continue;
-        double qx[KMAX], qy[KMAX];
         unsigned mx = 0, my = 0;  // bit u: this thread's column is s_u
-#pragma unroll
-        for (int u = 0; u < KMAX; ++u) {
-            qx[u] = qy[u] = 0.0;
-            if (u < t) {
-                const double2 q = *reinterpret_cast<const double2*>(B.qP + (int64_t)u * B.Cpad + j);
-                qx[u] = q.x;
-                qy[u] = q.y;
-                if (j == ss[u]) mx |= 1u << u;
-                if (j + 1 == ss[u]) my |= 1u << u;
-            }
+        bool special_rows = false;
+        for (int u = 0; u < t; ++u) {
+            if (j == ss[u]) mx |= 1u << u;
+            if (j + 1 == ss[u]) my |= 1u << u;
+            special_rows |= (sr[u] >= i0 && sr[u] < i0 + rows);
         }
         // does this tile hold a pivot row, or this thread a pivot column?  If not, the replay is t plain FMAs.
-        bool special_rows = false;
-        for (int u = 0; u < t; ++u) special_rows |= (sr[u] >= i0 && sr[u] < i0 + rows);
         const bool plain = !special_rows && mx == 0 && my == 0;
+        const double* qbase = B.qP + j;
         double* base = T + i0 * ld + j;
         for (int rr = 0; rr < rows; rr += BLK_UNROLL) {
             double2 v[BLK_UNROLL];
 #pragma unroll
             for (int w = 0; w < BLK_UNROLL; ++w)
                 if (rr + w < rows) v[w] = ld_stream(reinterpret_cast<const double2*>(base + (int64_t)(rr + w) * ld));
-            if (plain) {
+            for (int u0 = 0; u0 < t; u0 += BLK_CHUNK) {
+                double2 q[BLK_CHUNK];
 #pragma unroll
-                for (int u = 0; u < KMAX; ++u) {
-                    if (u < t) {
+                for (int k = 0; k < BLK_CHUNK; ++k)
+                    if (u0 + k < t) q[k] = *reinterpret_cast<const double2*>(qbase + (int64_t)(u0 + k) * B.Cpad);
+                if (plain) {
 #pragma unroll
-                        for (int w = 0; w < BLK_UNROLL; ++w) {
-                            const double nc = -scol[u][(rr + w) & (BLK_TILE_ROWS - 1)];
-                            v[w].x = __fma_rn(nc, qx[u], v[w].x);
-                            v[w].y = __fma_rn(nc, qy[u], v[w].y);
+                    for (int k = 0; k < BLK_CHUNK; ++k) {
+                        if (u0 + k < t) {
+#pragma unroll
+                            for (int w = 0; w < BLK_UNROLL; ++w) {
+                                const double nc = -scol[u0 + k][(rr + w) & (BLK_TILE_ROWS - 1)];
+                                v[w].x = __fma_rn(nc, q[k].x, v[w].x);
+                                v[w].y = __fma_rn(nc, q[k].y, v[w].y);
+                            }
                         }
                     }
-                }
-            } else {
+                } else {
 #pragma unroll
-                for (int u = 0; u < KMAX; ++u) {
-                    if (u < t) {
+                    for (int k = 0; k < BLK_CHUNK; ++k) {
+                        if (u0 + k < t) {
+                            const int u = u0 + k;
 #pragma unroll
-                        for (int w = 0; w < BLK_UNROLL; ++w) {
-                            const double c = scol[u][(rr + w) & (BLK_TILE_ROWS - 1)];
-                            const bool is_r = (i0 + rr + w == sr[u]);
-                            v[w].x = blk_step(v[w].x, is_r, (mx >> u) & 1u, c, qx[u], sinv[u]);
-                            v[w].y = blk_step(v[w].y, is_r, (my >> u) & 1u, c, qy[u], sinv[u]);
+                            for (int w = 0; w < BLK_UNROLL; ++w) {
+                                const double c = scol[u][(rr + w) & (BLK_TILE_ROWS - 1)];
+                                const bool is_r = (i0 + rr + w == sr[u]);
+                                v[w].x = blk_step(v[w].x, is_r, (mx >> u) & 1u, c, q[k].x, sinv[u]);
+                                v[w].y = blk_step(v[w].y, is_r, (my >> u) & 1u, c, q[k].y, sinv[u]);
+                            }
                         }
                     }
                 }
@@ -272,6 +382,11 @@ k_blk_flush(double* __restrict__ T, int64_t R, int64_t C, int64_t ld, const DevS
         }
     }
 }
-__global__ void k_blk_clear(const DevState* st, BlkBuffers B) { B.pend->base = st->n_pivots; }
+
+// after the flush: nothing pending, and the row part of the block's last pivot has been done by k_blk_row
+__global__ void k_blk_clear(DevState* st, BlkBuffers B) {
+    B.pend->base = st->n_pivots;
+    if (!st->done) st->have_pivot = 0;
+}
 
 }  // namespace b200lp

@@ -150,7 +150,7 @@ def test_generated_tableau_and_single_phases_bit_exact(solver, oracle, shape):
         np.testing.assert_array_equal(cl, ot.collab)
 
 
-@pytest.mark.parametrize("variant", [native.UPDATE_LDG, native.UPDATE_TMA, "onchip", "blocked3", "blocked8", "blocked16"])
+@pytest.mark.parametrize("variant", [native.UPDATE_LDG, native.UPDATE_TMA, "onchip", "blocked3", "blocked8", "blocked16", "blocked32"])
 @pytest.mark.parametrize("rule", [native.RULE_BLAND, native.RULE_DANTZIG])
 def test_device_loop_fixed_budget_bit_exact(solver, oracle, rule, variant):
     """Config 4 in miniature: a fixed pivot budget on a generated square tableau, Bland and Dantzig, through the
