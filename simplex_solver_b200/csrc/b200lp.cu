@@ -653,9 +653,8 @@ struct OnchipPlan {
 
 static bool onchip_plan(const b200lp_solver* s, OnchipPlan* plan) {
     if (s->C < 2 || s->snaps) return false;
-    int64_t gmax = s->sm_count;
-    if (const char* e = getenv("B200LP_ONCHIP_CTAS")) gmax = std::max<int64_t>(1, std::min<int64_t>(gmax, atoll(e)));  // tuning aid
-    const int64_t G = std::min<int64_t>(gmax, s->C - 1);
+    // one CTA per SM (measured on B200: 32..148 CTAs cost the same fixed latency per pivot; more CTAs = smaller slices)
+    const int64_t G = std::min<int64_t>(s->sm_count, s->C - 1);
     const int64_t wmax = (s->C - 1 + G - 1) / G;
     int64_t stride = wmax + 1;
     if ((stride & 1) == 0) ++stride;
