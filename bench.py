@@ -179,7 +179,8 @@ def workload_config(args):
         return {"workload": f"BASELINE config 4: single dense {args.rows}x{args.rows} fp64 condensed tableau, "
                             f"{args.rule} rule, fixed budget of {args.pivots} pivots per step",
                 "rows": args.rows, "cols": args.rows, "rule": args.rule, "pivots_per_step": args.pivots,
-                "bytes_per_pivot": 16 * args.rows * args.rows, "l2": "tableau (2.1 GB) is larger than L2 (126 MB)",
+                "bytes_per_pivot": 16 * args.rows * args.rows,
+                "l2": f"tableau ({8 * args.rows * args.rows / 1e9:.2f} GB) vs L2 (0.126 GB): every pivot streams it from HBM",
                 "parallelism": "1 GPU"}
     return {"workload": f"BASELINE config 5: single dense {args.rows}x{args.cols_total} fp64 condensed tableau "
                         f"column-sharded over {args.gpus} GPUs, {args.rule} rule, {args.pivots} pivots per step",
