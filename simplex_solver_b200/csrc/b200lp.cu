@@ -22,6 +22,7 @@
 #include "kernels_batched.cuh"
 #include "kernels_blocked.cuh"
 #include "kernels_build.cuh"
+#include "kernels_cluster.cuh"
 #include "kernels_onchip.cuh"
 #include "kernels_pick.cuh"
 #include "kernels_update.cuh"
@@ -145,6 +146,9 @@ struct b200lp_solver {
     double* snaps = nullptr;
     int64_t snap_cap = 0;
 
+    // CTAs per cluster of the single-launch pick kernel (kernels_cluster.cuh); 0 = not available / switched off
+    int cluster_ctas = 0;
+
     cudaGraphExec_t graph = nullptr;
     GraphKey graph_key;
     int64_t launches = 0;
@@ -200,6 +204,33 @@ B200LP_API int b200lp_create(b200lp_solver** out, int device) {
     CK(cudaFuncSetAttribute(k_update_tma<TMA_BOX_R, TMA_STAGES, TMA_STORE_LAG, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                             (int)TmaCfg<TMA_BOX_R, TMA_STAGES>::SMEM_BYTES));
     CK(cudaFuncSetAttribute(k_solve_onchip, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ONCHIP_SMEM_MAX));
+    if (!getenv("B200LP_NO_CLUSTER")) {  // diagnostic switch: fall back to the two-launch pick (k_price + k_ratio)
+        const void* kernels[4] = {(const void*)k_pick_cluster<false, false>, (const void*)k_pick_cluster<true, false>,
+                                  (const void*)k_pick_cluster<false, true>, (const void*)k_pick_cluster<true, true>};
+        for (int nc : {16, 8}) {
+            bool ok = true;
+            for (const void* kf : kernels) {
+                if (nc > 8 && cudaFuncSetAttribute(kf, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess) ok = false;
+                cudaLaunchConfig_t cfg = {};
+                cfg.gridDim = dim3(nc);
+                cfg.blockDim = dim3(CL_THREADS);
+                cudaLaunchAttribute at[1];
+                at[0].id = cudaLaunchAttributeClusterDimension;
+                at[0].val.clusterDim.x = nc;
+                at[0].val.clusterDim.y = 1;
+                at[0].val.clusterDim.z = 1;
+                cfg.attrs = at;
+                cfg.numAttrs = 1;
+                int n = 0;
+                if (!ok || cudaOccupancyMaxActiveClusters(&n, kf, &cfg) != cudaSuccess || n < 1) ok = false;
+            }
+            cudaGetLastError();  // a failed probe must not poison later calls
+            if (ok) {
+                s->cluster_ctas = nc;
+                break;
+            }
+        }
+    }
     CKR(s->gbar.ensure(1));
     CK(cudaStreamSynchronize(s->stream));
     *out = s;
@@ -504,6 +535,48 @@ static int launch_reset(b200lp_solver* s, int64_t max_pivots, bool keep_count) {
     return 0;
 }
 
+// both decisions of a pivot in one launch on one thread-block cluster (kernels_cluster.cuh)
+static int launch_pick_cluster(b200lp_solver* s, const b200lp_opts* o, int64_t obj_row, bool blocked) {
+    PickArgs A;
+    A.T = s->T;
+    A.R = s->R;
+    A.m = s->m;
+    A.C = s->C;
+    A.ld = s->ld;
+    A.obj_row = obj_row;
+    A.rowlab = s->rowlab.p;
+    A.collab = s->collab.p;
+    A.art_base = s->art_base;
+    A.eps_cost = o->eps_cost;
+    A.eps_pivot = o->eps_pivot;
+    A.st = s->st.p;
+    A.col = s->col.p;
+    A.B = s->blk;
+    A.h_row = s->h_row.p;
+    A.h_col = s->h_col.p;
+    A.h_enter = s->h_enter.p;
+    A.h_leave = s->h_leave.p;
+    A.hist_cap = s->hist_cap;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(s->cluster_ctas);
+    cfg.blockDim = dim3(CL_THREADS);
+    cfg.stream = s->stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = s->cluster_ctas;
+    at[0].val.clusterDim.y = 1;
+    at[0].val.clusterDim.z = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    const bool bland = o->rule == B200LP_RULE_BLAND;
+    cudaError_t e;
+    if (blocked) e = bland ? cudaLaunchKernelEx(&cfg, k_pick_cluster<true, true>, A) : cudaLaunchKernelEx(&cfg, k_pick_cluster<false, true>, A);
+    else e = bland ? cudaLaunchKernelEx(&cfg, k_pick_cluster<true, false>, A) : cudaLaunchKernelEx(&cfg, k_pick_cluster<false, false>, A);
+    if (e != cudaSuccess) return fail(B200LP_E_CUDA, "cluster pick launch failed: %s", cudaGetErrorString(e));
+    s->launches++;
+    return 0;
+}
+
 static int launch_snapshot(b200lp_solver* s) {
     if (!s->snaps) return 0;
     const int blocks = clampi((s->R * s->C + 255) / 256, 1, 4 * s->sm_count);
@@ -515,8 +588,12 @@ static int launch_snapshot(b200lp_solver* s) {
 
 // one iteration of the loop on the stream
 static int enqueue_iteration(b200lp_solver* s, const b200lp_opts* o, int64_t obj_row) {
-    CKR(launch_price(s, obj_row, o->rule, o->eps_cost, false));
-    CKR(launch_ratio(s, o->eps_pivot, false, nullptr, 0));
+    if (s->cluster_ctas) {
+        CKR(launch_pick_cluster(s, o, obj_row, false));
+    } else {
+        CKR(launch_price(s, obj_row, o->rule, o->eps_cost, false));
+        CKR(launch_ratio(s, o->eps_pivot, false, nullptr, 0));
+    }
     CKR(launch_update(s, o->update_variant));
     CKR(launch_snapshot(s));
     return 0;
@@ -557,6 +634,7 @@ static int blk_block_size(const b200lp_opts* o) {
 
 // one look-ahead pivot = two launches: [row part of the previous pivot + pricing] and [ratio on the replayed column]
 static int enqueue_blk_pick(b200lp_solver* s, const b200lp_opts* o, int64_t obj_row) {
+    if (s->cluster_ctas) return launch_pick_cluster(s, o, obj_row, true);
     const int wb = clampi((std::max(s->R, s->C) + BLK_THREADS * 2 - 1) / (BLK_THREADS * 2), 1, 2 * s->sm_count);
     if (o->rule == B200LP_RULE_BLAND)
         k_blk_rowprice<true><<<wb, BLK_THREADS, 0, s->stream>>>(s->T, s->R, s->C, s->ld, obj_row, s->collab.p, s->art_base,
@@ -723,7 +801,8 @@ static int run_loop(b200lp_solver* s, const b200lp_opts* o, int64_t obj_row, int
     }
     const bool use_graph = o->loop_mode != B200LP_LOOP_LAUNCHES && mode == 0 && s->stream != (cudaStream_t)0;
     if (use_graph) CKR(get_graph(s, o, obj_row, iters, blocked_k));
-    const int per_iter = blocked_k ? 2 * blocked_k + 3 : (s->snaps ? 4 : 3);
+    const int picks = s->cluster_ctas ? 1 : 2;  // launches per pick
+    const int per_iter = blocked_k ? picks * blocked_k + 3 : picks + 1 + (s->snaps ? 1 : 0);
     int slot = 0;
     bool first = true;
     for (;;) {
@@ -1125,9 +1204,14 @@ B200LP_API int b200lp_profile_loop(b200lp_solver* s, const b200lp_opts* o, int64
     for (auto& e : ev) CK(cudaEventCreate(&e));
     for (int i = 0; i < iters; ++i) {
         CK(cudaEventRecord(ev[(size_t)i * 4 + 0], s->stream));
-        CKR(launch_price(s, obj_row, o->rule, o->eps_cost, false));
-        CK(cudaEventRecord(ev[(size_t)i * 4 + 1], s->stream));
-        CKR(launch_ratio(s, o->eps_pivot, false, nullptr, 0));
+        if (s->cluster_ctas) {  // one launch takes both decisions: reported as "price", "ratio" = 0
+            CKR(launch_pick_cluster(s, o, obj_row, false));
+            CK(cudaEventRecord(ev[(size_t)i * 4 + 1], s->stream));
+        } else {
+            CKR(launch_price(s, obj_row, o->rule, o->eps_cost, false));
+            CK(cudaEventRecord(ev[(size_t)i * 4 + 1], s->stream));
+            CKR(launch_ratio(s, o->eps_pivot, false, nullptr, 0));
+        }
         CK(cudaEventRecord(ev[(size_t)i * 4 + 2], s->stream));
         CKR(launch_update(s, o->update_variant));
         CK(cudaEventRecord(ev[(size_t)i * 4 + 3], s->stream));

@@ -307,7 +307,7 @@ k_blk_flush(double* __restrict__ T, int64_t R, int64_t C, int64_t ld, const DevS
             int tiles_c, int64_t n_tiles) {
     __shared__ int32_t sr[BLK_KMAX], ss[BLK_KMAX];
     __shared__ double sinv[BLK_KMAX];
-    __shared__ double scol[BLK_KMAX][BLK_TILE_ROWS];
+    __shared__ __align__(16) double scol[BLK_KMAX][BLK_TILE_ROWS];
     const int t = (int)(st->n_pivots - B.pend->base);
     if (t == 0) return;
     if (threadIdx.x < t) {
@@ -348,7 +348,21 @@ k_blk_flush(double* __restrict__ T, int64_t R, int64_t C, int64_t ld, const DevS
 #pragma unroll
                 for (int k = 0; k < BLK_CHUNK; ++k)
                     if (u0 + k < t) q[k] = *reinterpret_cast<const double2*>(qbase + (int64_t)(u0 + k) * B.Cpad);
-                if (plain) {
+                if (plain && u0 + BLK_CHUNK <= t) {
+                    // full chunk, no pivot row / column in sight: 4 x LDS.128 + 16 x DFMA per step for the 8 rows
+                    static_assert(BLK_UNROLL == 8, "the vectorised column reads below assume 8 rows per group");
+#pragma unroll
+                    for (int k = 0; k < BLK_CHUNK; ++k) {
+                        const double2* sc = reinterpret_cast<const double2*>(&scol[u0 + k][rr]);
+                        const double2 c01 = sc[0], c23 = sc[1], c45 = sc[2], c67 = sc[3];
+                        const double c[8] = {c01.x, c01.y, c23.x, c23.y, c45.x, c45.y, c67.x, c67.y};
+#pragma unroll
+                        for (int w = 0; w < BLK_UNROLL; ++w) {
+                            v[w].x = __fma_rn(-c[w], q[k].x, v[w].x);
+                            v[w].y = __fma_rn(-c[w], q[k].y, v[w].y);
+                        }
+                    }
+                } else if (plain) {
 #pragma unroll
                     for (int k = 0; k < BLK_CHUNK; ++k) {
                         if (u0 + k < t) {
