@@ -450,6 +450,10 @@ def secondary_configs(args):
     return out
 
 
+def opts_la(native, rule, n):
+    return native.make_opts(rule=rule, max_pivots=n)
+
+
 def bench_sharded(args):
     import torch
     import torch.distributed as dist
@@ -526,6 +530,27 @@ def _bench_sharded(args, rank, local, world):
                 "loop_frac_of_peak_per_gpu": value * bytes_per_pivot / 1e9 / world / peak,
                 "loop_frac_of_nominal_8TBs_per_gpu": value * bytes_per_pivot / 1e9 / world / 8000.0}
 
+    # beyond the rank-1 roofline: the look-ahead loop on the sharded tableau (same exchange per pivot, one tableau
+    # pass per K pivots; bit-identical pivots, tests/nccl_sharded_check.py)
+    lookahead = None
+    if args.lookahead:
+        lookahead = {}
+        for K in (16, 32):
+            n_la = 2 * K
+            drv.run(opts_la(native, rule, n_la), n_la, check_every=K, lookahead=K)   # warm-up + graph capture
+            torch.cuda.synchronize()
+            dist.barrier()
+            a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a0.record()
+            _, got = drv.run(opts_la(native, rule, n_la), n_la, check_every=K, lookahead=K)
+            a1.record()
+            torch.cuda.synchronize()
+            tl = torch.tensor([a0.elapsed_time(a1) * 1e-3], dtype=torch.float64, device=f"cuda:{local}")
+            dist.all_reduce(tl, op=dist.ReduceOp.MAX)
+            pps = got / float(tl.item())
+            lookahead[f"K={K}"] = {"pivots_per_s": pps, "speedup_vs_rank1_loop": pps / value,
+                                   "hbm_bytes_per_pivot": bytes_per_pivot / K}
+
     # e2e: inputs of this config cannot be staged through the host (137 GB); the end-to-end pass regenerates the
     # shard on the device inside the timed region and reads x*, z back to the host.
     del drv
@@ -557,6 +582,8 @@ def _bench_sharded(args, rank, local, world):
             "cpu_baseline": None, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
             "collective": {"op": "all_gather_into_tensor (NCCL)", "bytes_per_rank_per_pivot": 8 * (R + 2)},
         }
+        if lookahead:
+            line["lookahead"] = lookahead
         print(json.dumps(line))
 
 

@@ -173,6 +173,14 @@ int b200lp_shard_candidate(b200lp_solver *s, const b200lp_opts *o, int64_t obj_r
 /* gathered_dev: world x (R + 2) doubles; picks the global entering column, runs ratio test + update     */
 int b200lp_shard_pivot(b200lp_solver *s, const b200lp_opts *o, const double *gathered_dev, int32_t world,
                        int32_t rank);
+/* look-ahead (B200LP_LOOP_BLOCKED) form of the same protocol: begin once per run (after shard_reset), then per pivot
+ * blk_candidate -> all-gather -> blk_pivot, and blk_flush after every K <= 32 pivots and at the end of the run (the
+ * tableau is only up to date after a flush)                                                                  */
+int b200lp_shard_blk_begin(b200lp_solver *s, int64_t obj_row);
+int b200lp_shard_blk_candidate(b200lp_solver *s, const b200lp_opts *o, int64_t obj_row, double *cand_dev);
+int b200lp_shard_blk_pivot(b200lp_solver *s, const b200lp_opts *o, const double *gathered_dev, int32_t world,
+                           int32_t rank);
+int b200lp_shard_blk_flush(b200lp_solver *s, int64_t obj_row);
 /* synchronise and read the loop state of a sharded run */
 int b200lp_shard_state(b200lp_solver *s, int32_t *done, int32_t *status, int64_t *n_pivots);
 int b200lp_shard_reset(b200lp_solver *s, int64_t max_pivots);

@@ -632,22 +632,39 @@ static int blk_block_size(const b200lp_opts* o) {
     return o->check_every > 0 ? (int)std::max(1, std::min(BLK_KMAX, o->check_every)) : 8;
 }
 
-// one look-ahead pivot = two launches: [row part of the previous pivot + pricing] and [ratio on the replayed column]
-static int enqueue_blk_pick(b200lp_solver* s, const b200lp_opts* o, int64_t obj_row) {
-    if (s->cluster_ctas) return launch_pick_cluster(s, o, obj_row, true);
+static int launch_blk_rowprice(b200lp_solver* s, const b200lp_opts* o, int64_t obj_row, bool sharded) {
     const int wb = clampi((std::max(s->R, s->C) + BLK_THREADS * 2 - 1) / (BLK_THREADS * 2), 1, 2 * s->sm_count);
-    if (o->rule == B200LP_RULE_BLAND)
-        k_blk_rowprice<true><<<wb, BLK_THREADS, 0, s->stream>>>(s->T, s->R, s->C, s->ld, obj_row, s->collab.p, s->art_base,
-                                                               o->eps_cost, s->st.p, s->part_price.p, s->blk);
-    else
-        k_blk_rowprice<false><<<wb, BLK_THREADS, 0, s->stream>>>(s->T, s->R, s->C, s->ld, obj_row, s->collab.p, s->art_base,
-                                                                o->eps_cost, s->st.p, s->part_price.p, s->blk);
+#define ROWPRICE(BL, SH) \
+    k_blk_rowprice<BL, SH><<<wb, BLK_THREADS, 0, s->stream>>>(s->T, s->R, s->C, s->ld, obj_row, s->collab.p, s->art_base, o->eps_cost, s->st.p, s->part_price.p, s->blk)
+    if (o->rule == B200LP_RULE_BLAND) {
+        if (sharded) ROWPRICE(true, true);
+        else ROWPRICE(true, false);
+    } else {
+        if (sharded) ROWPRICE(false, true);
+        else ROWPRICE(false, false);
+    }
+#undef ROWPRICE
+    s->launches++;
+    CK(cudaGetLastError());
+    return 0;
+}
+
+static int launch_blk_ratio(b200lp_solver* s, const b200lp_opts* o, const double* ext, int64_t ext_stride) {
     const int rb = clampi((s->R + BLK_THREADS - 1) / BLK_THREADS, 1, 2 * s->sm_count);
     k_blk_ratio<<<rb, BLK_THREADS, 0, s->stream>>>(s->T, s->R, s->m, s->C, s->ld, s->rowlab.p, s->collab.p, o->eps_pivot, s->st.p,
-                                                 s->part_ratio.p, s->blk, s->h_row.p, s->h_col.p, s->h_enter.p, s->h_leave.p,
-                                                 s->hist_cap);
-    s->launches += 2;
+                                                 s->part_ratio.p, s->blk, ext, ext_stride, s->h_row.p, s->h_col.p,
+                                                 s->h_enter.p, s->h_leave.p, s->hist_cap);
+    s->launches++;
     CK(cudaGetLastError());
+    return 0;
+}
+
+// one look-ahead pivot: one launch on a thread-block cluster, or [row part of the previous pivot + pricing] and
+// [ratio on the replayed column]
+static int enqueue_blk_pick(b200lp_solver* s, const b200lp_opts* o, int64_t obj_row) {
+    if (s->cluster_ctas) return launch_pick_cluster(s, o, obj_row, true);
+    CKR(launch_blk_rowprice(s, o, obj_row, false));
+    CKR(launch_blk_ratio(s, o, nullptr, 0));
     return 0;
 }
 
@@ -1275,6 +1292,54 @@ B200LP_API int b200lp_shard_pivot(b200lp_solver* s, const b200lp_opts* o, const 
     CK(cudaGetLastError());
     CKR(launch_ratio(s, o->eps_pivot, false, gathered_dev, stride));
     CKR(launch_update(s, o->update_variant));
+    return 0;
+}
+
+// ---- look-ahead (blocked) loop on a column shard: same exchange per pivot, one tableau pass per K pivots ----
+B200LP_API int b200lp_shard_blk_begin(b200lp_solver* s, int64_t obj_row) {
+    if (!s || !s->T) return fail(B200LP_E_STATE, "no tableau bound");
+    if (obj_row < s->m || obj_row >= s->R) return fail(B200LP_E_INVALID, "obj_row %lld is not an objective row", (long long)obj_row);
+    CKR(set_device(s));
+    CKR(launch_flush(s));
+    CKR(blk_setup(s));
+    const int ib = clampi((std::max(s->R, s->C) + BLK_THREADS - 1) / BLK_THREADS, 1, 2 * s->sm_count);
+    k_blk_init<<<ib, BLK_THREADS, 0, s->stream>>>(s->T, s->R, s->C, s->ld, obj_row, s->st.p, s->blk);
+    s->launches++;
+    CK(cudaGetLastError());
+    return 0;
+}
+
+B200LP_API int b200lp_shard_blk_candidate(b200lp_solver* s, const b200lp_opts* o, int64_t obj_row, double* cand_dev) {
+    if (!s || !s->T) return fail(B200LP_E_STATE, "no tableau bound");
+    if (!cand_dev) return fail(B200LP_E_INVALID, "cand_dev is NULL");
+    CKR(check_opts(o));
+    CKR(set_device(s));
+    CKR(launch_blk_rowprice(s, o, obj_row, true));
+    const int blocks = clampi((s->R + BLK_THREADS - 1) / BLK_THREADS, 1, 2 * s->sm_count);
+    k_blk_shard_extract<<<blocks, BLK_THREADS, 0, s->stream>>>(s->T, s->R, s->ld, s->st.p, s->blk, cand_dev);
+    s->launches++;
+    CK(cudaGetLastError());
+    return 0;
+}
+
+B200LP_API int b200lp_shard_blk_pivot(b200lp_solver* s, const b200lp_opts* o, const double* gathered_dev, int32_t world,
+                                      int32_t rank) {
+    if (!s || !s->T) return fail(B200LP_E_STATE, "no tableau bound");
+    if (!gathered_dev || world < 1 || rank < 0 || rank >= world) return fail(B200LP_E_INVALID, "bad shard arguments");
+    CKR(check_opts(o));
+    CKR(set_device(s));
+    const int64_t stride = s->R + 2;
+    k_shard_winner<<<1, 32, 0, s->stream>>>(gathered_dev, stride, world, rank, o->rule == B200LP_RULE_BLAND, s->st.p);
+    s->launches++;
+    CK(cudaGetLastError());
+    CKR(launch_blk_ratio(s, o, gathered_dev, stride));
+    return 0;
+}
+
+B200LP_API int b200lp_shard_blk_flush(b200lp_solver* s, int64_t obj_row) {
+    if (!s || !s->T) return fail(B200LP_E_STATE, "no tableau bound");
+    CKR(set_device(s));
+    CKR(enqueue_blk_flush(s, BLK_KMAX, obj_row));
     return 0;
 }
 

@@ -58,10 +58,12 @@ k_blk_init(const double* __restrict__ T, int64_t R, int64_t C, int64_t ld, int64
 
 // Ratio test of the look-ahead pivot: the entering column is gathered from the stored tableau and brought up to date
 // by replaying the pending steps; it is kept as col_t.  Same ticket pattern and bookkeeping as k_ratio.
+// `ext` (sharded tableaux): the gathered candidates; the winner's column arrives already up to date, so it is copied
+// instead of gathered + replayed, and st->s is -1 on the shards that do not own it.
 __global__ void __launch_bounds__(BLK_THREADS)
 k_blk_ratio(const double* __restrict__ T, int64_t R, int64_t m, int64_t C, int64_t ld, int32_t* rowlab, int32_t* collab,
-            double eps_pivot, DevState* st, Key* partials, BlkBuffers B, int32_t* h_row, int32_t* h_col,
-            int32_t* h_enter, int32_t* h_leave, int64_t hist_cap) {
+            double eps_pivot, DevState* st, Key* partials, BlkBuffers B, const double* __restrict__ ext,
+            int64_t ext_stride, int32_t* h_row, int32_t* h_col, int32_t* h_enter, int32_t* h_leave, int64_t hist_cap) {
     __shared__ Key sk[BLK_THREADS / 32];
     __shared__ bool is_last;
     __shared__ int32_t sr[BLK_KMAX], ss[BLK_KMAX];
@@ -69,7 +71,8 @@ k_blk_ratio(const double* __restrict__ T, int64_t R, int64_t m, int64_t C, int64
     if (st->done || !st->have_pivot) return;
     const int s = st->s;
     const int t = (int)(st->n_pivots - B.pend->base);  // this kernel's last CTA increments n_pivots at its very end
-    if (threadIdx.x < t) {
+    const double* src = ext ? ext + (int64_t)st->win_rank * ext_stride + 2 : nullptr;
+    if (!src && threadIdx.x < t) {
         sr[threadIdx.x] = B.pend->r[threadIdx.x];
         ss[threadIdx.x] = B.pend->s[threadIdx.x];
         sinv[threadIdx.x] = B.pend->inv_p[threadIdx.x];
@@ -80,9 +83,14 @@ k_blk_ratio(const double* __restrict__ T, int64_t R, int64_t m, int64_t C, int64
     const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, nthr = (int64_t)gridDim.x * blockDim.x;
     Key k = key_none();
     for (int64_t i = tid; i < R; i += nthr) {
-        double a = T[i * ld + s];
-        for (int u = 0; u < t; ++u)
-            a = blk_step(a, i == sr[u], s == ss[u], B.colP[(int64_t)u * B.Rpad + i], sq[u], sinv[u]);
+        double a;
+        if (src) {
+            a = src[i];
+        } else {
+            a = T[i * ld + s];
+            for (int u = 0; u < t; ++u)
+                a = blk_step(a, i == sr[u], s == ss[u], B.colP[(int64_t)u * B.Rpad + i], sq[u], sinv[u]);
+        }
         colT[i] = a;
         if (i < m) {
             const int32_t lab = rowlab[i];
@@ -137,7 +145,7 @@ k_blk_ratio(const double* __restrict__ T, int64_t R, int64_t m, int64_t C, int64
             const int32_t leave = rowlab[r];
             st->leave_lab = leave;
             rowlab[r] = st->enter_lab;
-            collab[s] = leave;
+            if (s >= 0) collab[s] = leave;
             const long long n = st->n_pivots;
             if (n < hist_cap) {
                 h_row[n] = r;
@@ -146,6 +154,7 @@ k_blk_ratio(const double* __restrict__ T, int64_t R, int64_t m, int64_t C, int64
                 h_leave[n] = leave;
             }
             st->n_pivots = n + 1;
+            st->pend = 1;  // look-ahead loops: "the row part of this pivot is due" (cleared by whoever does it)
         }
     }
 }
@@ -156,7 +165,7 @@ __global__ void __launch_bounds__(BLK_THREADS)
 k_blk_row(const double* __restrict__ T, int64_t R, int64_t C, int64_t ld, int64_t obj_row, DevState* st, BlkBuffers B) {
     __shared__ int32_t sr[BLK_KMAX], ss[BLK_KMAX];
     __shared__ double sinv[BLK_KMAX], sc[BLK_KMAX];
-    if (st->done || !st->have_pivot) return;
+    if (!st->pend) return;  // the flag is cleared by k_blk_clear, after the flush
     const int t = (int)(st->n_pivots - 1 - B.pend->base);
     const int r = st->r, s = st->s;
     const double p = st->p, inv_p = st->inv_p;
@@ -186,8 +195,9 @@ k_blk_row(const double* __restrict__ T, int64_t R, int64_t C, int64_t ld, int64_
 
 // Fused "row part of the previous look-ahead pivot" + "pricing of the next one": the thread that refreshes objcur[j]
 // prices it at once, so a look-ahead pivot costs two launches (this one and k_blk_ratio) instead of three.
-// DevState.have_pivot == 1 on entry means k_blk_ratio recorded a pivot whose row part is still due.
-template <bool BLAND>
+// DevState.pend == 1 on entry means k_blk_ratio recorded a pivot whose row part is still due.  SHARDED: "no local
+// candidate" does not end the loop (k_shard_winner decides after the all-gather).
+template <bool BLAND, bool SHARDED>
 __global__ void __launch_bounds__(BLK_THREADS)
 k_blk_rowprice(const double* __restrict__ T, int64_t R, int64_t C, int64_t ld, int64_t obj_row,
                const int32_t* __restrict__ collab, int32_t art_base, double eps_cost, DevState* st, Key* partials,
@@ -197,7 +207,7 @@ k_blk_rowprice(const double* __restrict__ T, int64_t R, int64_t C, int64_t ld, i
     __shared__ int32_t sr[BLK_KMAX], ss[BLK_KMAX];
     __shared__ double sinv[BLK_KMAX], sc[BLK_KMAX];
     if (st->done) return;
-    const bool row_due = st->have_pivot != 0;
+    const bool row_due = st->pend != 0;
     const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, nthr = (int64_t)gridDim.x * blockDim.x;
     Key k = key_none();
     if (row_due) {
@@ -274,16 +284,19 @@ k_blk_rowprice(const double* __restrict__ T, int64_t R, int64_t C, int64_t ld, i
     }
     if (threadIdx.x == 0) {
         st->ticket_price = 0;
+        st->pend = 0;  // the row part (if any) is done
         if (st->n_pivots >= st->max_pivots) {
             st->done = 1;
             st->status = 1;  // LIMIT
             st->have_pivot = 0;
         } else if (k.lab == B200LP_NO_LAB) {
-            st->done = 1;
-            st->status = 0;  // OPTIMAL for this objective row
             st->have_pivot = 0;
             st->s = -1;
             st->enter_lab = -1;
+            if (!SHARDED) {  // sharded: another shard may still have a candidate (k_shard_winner decides)
+                st->done = 1;
+                st->status = 0;  // OPTIMAL for this objective row
+            }
         } else {
             st->have_pivot = 1;
             st->s = k.pos;
@@ -400,7 +413,37 @@ k_blk_flush(double* __restrict__ T, int64_t R, int64_t C, int64_t ld, const DevS
 // after the flush: nothing pending, and the row part of the block's last pivot has been done by k_blk_row
 __global__ void k_blk_clear(DevState* st, BlkBuffers B) {
     B.pend->base = st->n_pivots;
-    if (!st->done) st->have_pivot = 0;
+    st->pend = 0;
+}
+
+// Sharded look-ahead: publish this shard's candidate [reduced cost, variable id, column brought up to date].
+__global__ void __launch_bounds__(BLK_THREADS)
+k_blk_shard_extract(const double* __restrict__ T, int64_t R, int64_t ld, const DevState* st, BlkBuffers B,
+                    double* __restrict__ cand) {
+    __shared__ int32_t sr[BLK_KMAX], ss[BLK_KMAX];
+    __shared__ double sinv[BLK_KMAX], sq[BLK_KMAX];
+    const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int have = st->have_pivot && !st->done;
+    if (tid == 0) {
+        cand[0] = have ? st->best_val : 0.0;
+        cand[1] = have ? (double)st->enter_lab : -1.0;
+    }
+    if (!have) return;
+    const int s = st->s;
+    const int t = (int)(st->n_pivots - B.pend->base);
+    if (threadIdx.x < t) {
+        sr[threadIdx.x] = B.pend->r[threadIdx.x];
+        ss[threadIdx.x] = B.pend->s[threadIdx.x];
+        sinv[threadIdx.x] = B.pend->inv_p[threadIdx.x];
+        sq[threadIdx.x] = B.qP[(int64_t)threadIdx.x * B.Cpad + s];
+    }
+    __syncthreads();
+    for (int64_t i = tid; i < R; i += (int64_t)gridDim.x * blockDim.x) {
+        double a = T[i * ld + s];
+        for (int u = 0; u < t; ++u)
+            a = blk_step(a, i == sr[u], s == ss[u], B.colP[(int64_t)u * B.Rpad + i], sq[u], sinv[u]);
+        cand[2 + i] = a;
+    }
 }
 
 }  // namespace b200lp

@@ -72,7 +72,7 @@ __global__ void __launch_bounds__(CL_THREADS, 1) k_pick_cluster(const PickArgs A
     // ------------------------------------------------ phase A: columns ------------------------------------------------
     Key k = key_none();
     if (BLOCKED) {
-        const bool row_due = st->have_pivot != 0;
+        const bool row_due = st->pend != 0;
         if (row_due) {
             const int t = (int)(n_piv - 1 - base);
             const int r = st->r, s = st->s;
@@ -226,9 +226,8 @@ __global__ void __launch_bounds__(CL_THREADS, 1) k_pick_cluster(const PickArgs A
         A.B.pend->s[t] = s;
         A.B.pend->inv_p[t] = inv_p;
         A.B.pend->q_rhs = __ldcg(A.B.rhscur + r) / p;
-    } else {
-        st->pend = 1;
     }
+    st->pend = 1;  // rank-1: row r awaits its scaling; look-ahead: the row part of this pivot is due
     const int32_t leave = A.rowlab[r];
     st->leave_lab = leave;
     A.rowlab[r] = win.lab;

@@ -35,7 +35,8 @@ EXPORTS = [
     "b200lp_run", "b200lp_solve", "b200lp_select_entering", "b200lp_ratio_test", "b200lp_pivot",
     "b200lp_shard_candidate", "b200lp_shard_pivot", "b200lp_shard_state", "b200lp_shard_reset",
     "b200lp_read_history", "b200lp_solve_batched", "b200lp_time_update", "b200lp_build_dense",
-    "b200lp_set_snapshots", "b200lp_profile_loop", "b200lp_use_own_stream",
+    "b200lp_set_snapshots", "b200lp_profile_loop", "b200lp_use_own_stream", "b200lp_shard_blk_begin",
+    "b200lp_shard_blk_candidate", "b200lp_shard_blk_pivot", "b200lp_shard_blk_flush",
 ]
 
 _f64p = C.POINTER(C.c_double)
@@ -125,6 +126,10 @@ def lib():
                 L.b200lp_pivot.argtypes = [C.c_void_p, C.c_int64, C.c_int64, C.c_int32]
                 L.b200lp_shard_candidate.argtypes = [C.c_void_p, C.POINTER(Opts), C.c_int64, C.c_void_p]
                 L.b200lp_shard_pivot.argtypes = [C.c_void_p, C.POINTER(Opts), C.c_void_p, C.c_int32, C.c_int32]
+                L.b200lp_shard_blk_begin.argtypes = [C.c_void_p, C.c_int64]
+                L.b200lp_shard_blk_candidate.argtypes = [C.c_void_p, C.POINTER(Opts), C.c_int64, C.c_void_p]
+                L.b200lp_shard_blk_pivot.argtypes = [C.c_void_p, C.POINTER(Opts), C.c_void_p, C.c_int32, C.c_int32]
+                L.b200lp_shard_blk_flush.argtypes = [C.c_void_p, C.c_int64]
                 L.b200lp_shard_state.argtypes = [C.c_void_p, C.POINTER(C.c_int32), C.POINTER(C.c_int32),
                                                  C.POINTER(C.c_int64)]
                 L.b200lp_shard_reset.argtypes = [C.c_void_p, C.c_int64]
@@ -354,6 +359,18 @@ class Solver:
 
     def shard_pivot(self, opts: Opts, gathered_ptr: int, world: int, rank: int):
         check(lib().b200lp_shard_pivot(self._h, C.byref(opts), C.c_void_p(gathered_ptr), world, rank))
+
+    def shard_blk_begin(self, obj_row: int):
+        check(lib().b200lp_shard_blk_begin(self._h, obj_row))
+
+    def shard_blk_candidate(self, opts: Opts, obj_row: int, cand_ptr: int):
+        check(lib().b200lp_shard_blk_candidate(self._h, C.byref(opts), obj_row, C.c_void_p(cand_ptr)))
+
+    def shard_blk_pivot(self, opts: Opts, gathered_ptr: int, world: int, rank: int):
+        check(lib().b200lp_shard_blk_pivot(self._h, C.byref(opts), C.c_void_p(gathered_ptr), world, rank))
+
+    def shard_blk_flush(self, obj_row: int):
+        check(lib().b200lp_shard_blk_flush(self._h, obj_row))
 
     def shard_state(self):
         done, status, n = C.c_int32(), C.c_int32(), C.c_int64()

@@ -65,12 +65,25 @@ class CudaShardEngine:
             self.solver.set_stream(outer)
         return g
 
-    def candidate(self, opts):
-        self.solver.shard_candidate(opts, self.m, self.cand.data_ptr())
+    def candidate(self, opts, lookahead: bool = False):
+        if lookahead:
+            self.solver.shard_blk_candidate(opts, self.m, self.cand.data_ptr())
+        else:
+            self.solver.shard_candidate(opts, self.m, self.cand.data_ptr())
         return self.cand
 
-    def pivot(self, opts, gathered, world, rank):
-        self.solver.shard_pivot(opts, gathered.data_ptr(), world, rank)
+    def pivot(self, opts, gathered, world, rank, lookahead: bool = False):
+        if lookahead:
+            self.solver.shard_blk_pivot(opts, gathered.data_ptr(), world, rank)
+        else:
+            self.solver.shard_pivot(opts, gathered.data_ptr(), world, rank)
+
+    # look-ahead loop (kernels_blocked.cuh): pivots are decided from O(R + C) state and applied K at a time
+    def lookahead_begin(self):
+        self.solver.shard_blk_begin(self.m)
+
+    def lookahead_flush(self):
+        self.solver.shard_blk_flush(self.m)
 
     def state(self):
         return self.solver.shard_state()
@@ -108,32 +121,45 @@ class ShardedTableau:
         import torch.distributed as dist
         dist.all_gather_into_tensor(self.gathered, cand, group=self.group)
 
-    def _chunk(self, opts, n):
+    def _chunk(self, opts, n, lookahead=0):
         eng = self.engine
-        for _ in range(n):
-            self._all_gather(eng.candidate(opts))
-            eng.pivot(opts, self.gathered, self.world, self.rank)
+        for i in range(n):
+            self._all_gather(eng.candidate(opts, lookahead > 0) if lookahead else eng.candidate(opts))
+            if lookahead:
+                eng.pivot(opts, self.gathered, self.world, self.rank, True)
+                if (i + 1) % lookahead == 0 or i + 1 == n:
+                    eng.lookahead_flush()
+            else:
+                eng.pivot(opts, self.gathered, self.world, self.rank)
 
-    def run(self, opts, max_pivots: int, check_every: int = 0, use_graph: bool = True):
+    def run(self, opts, max_pivots: int, check_every: int = 0, use_graph: bool = True, lookahead: int = 0):
         """Enqueue pivots until optimal / unbounded / max_pivots.  Returns (status, n_pivots).
 
         On GPUs the per-pivot sequence (candidate kernels -> NCCL all-gather -> winner / ratio / update kernels) of a
         whole chunk is captured once into a CUDA graph and replayed, so the host issues one launch per `check_every`
         pivots instead of ~8 calls per pivot; the first chunk runs eagerly (it also warms NCCL up for capture).
+
+        lookahead = K > 0 selects the look-ahead loop: the exchange per pivot is the same, but the tableau is only
+        touched once per K pivots (one flush); pivots and tableau stay bit-identical.
         """
         eng = self.engine
         eng.reset(max_pivots)
+        lookahead = int(max(0, min(lookahead, 32)))
+        if lookahead:
+            eng.lookahead_begin()
         check_every = check_every or max(1, min(max_pivots, 64))
-        key = (opts.rule, opts.update_variant, opts.eps_cost, opts.eps_pivot, check_every)
+        if lookahead:
+            check_every = max(lookahead, check_every // lookahead * lookahead)  # whole blocks per chunk
+        key = (opts.rule, opts.update_variant, opts.eps_cost, opts.eps_pivot, check_every, lookahead)
         graph = self._graphs.get(key) if use_graph else None
         done_total = 0
         while True:
             if graph is not None:
                 graph.replay()
             else:
-                self._chunk(opts, check_every)
+                self._chunk(opts, check_every, lookahead)
                 if use_graph and hasattr(eng, "capture_chunk") and key not in self._graphs:
-                    self._graphs[key] = eng.capture_chunk(lambda: self._chunk(opts, check_every))
+                    self._graphs[key] = eng.capture_chunk(lambda: self._chunk(opts, check_every, lookahead))
                     graph = self._graphs[key]
             done_total += check_every
             done, status, n = eng.state()

@@ -24,7 +24,14 @@ class OracleShardEngine:
         self.done, self.status, self.n, self.max_pivots = False, 0, 0, max_pivots
         self.hist = []
 
-    def candidate(self, opts):
+    # the look-ahead loop changes WHEN the tableau is touched, not the protocol: the CPU stand-in ignores it
+    def lookahead_begin(self):
+        pass
+
+    def lookahead_flush(self):
+        pass
+
+    def candidate(self, opts, lookahead=False):
         c = self.cand.numpy()
         c[:] = 0.0
         c[1] = -1.0
@@ -42,7 +49,7 @@ class OracleShardEngine:
             c[2:] = self.t.extract_col(s)
         return self.cand
 
-    def pivot(self, opts, gathered, world, rank):
+    def pivot(self, opts, gathered, world, rank, lookahead=False):
         if self.done:
             return
         g = gathered.numpy().reshape(world, self.R + 2)

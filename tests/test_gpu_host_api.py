@@ -149,6 +149,19 @@ def test_cuda_shard_engine_world1_and_emulated_world2(oracle, rule):
     np.testing.assert_array_equal(h["enter_lab"], ref["enter_lab"])
     assert_bit_equal(eng.tableau(), one.T, "world-1 shard tableau")
 
+    # world = 1 again through the look-ahead loop (K = 7: ragged last block)
+    eng = CudaShardEngine(m, n_total, 0, n_total, seed)
+    status, n = ShardedTableau(eng, 1, 0).run(opts, budget, check_every=21, lookahead=7)
+    assert status == ref["status"] and n == ref["n_pivots"]
+    np.testing.assert_array_equal(eng.history(budget)["piv_row"], ref["piv_row"])
+    assert_bit_equal(eng.tableau(), one.T, "world-1 shard tableau, look-ahead")
+
+    for lookahead in (0, 6):
+        _emulated_two_shards(oracle, one, ref, opts, m, n_total, seed, budget, lookahead)
+
+
+def _emulated_two_shards(oracle, one, ref, opts, m, n_total, seed, budget, lookahead):
+    import torch
     world = 2
     engs = []
     for r in range(world):
@@ -157,14 +170,21 @@ def test_cuda_shard_engine_world1_and_emulated_world2(oracle, rule):
     gathered = engs[0].new_buffer(world)
     for e in engs:
         e.reset(budget)
+        if lookahead:
+            e.lookahead_begin()
     stride = m + 1 + 2
-    for _ in range(budget + 2):
+    for it in range(budget + 2):
         for r, e in enumerate(engs):
-            gathered[r * stride:(r + 1) * stride].copy_(e.candidate(opts))
+            gathered[r * stride:(r + 1) * stride].copy_(e.candidate(opts, lookahead > 0))
         torch.cuda.synchronize()
         for r, e in enumerate(engs):
-            e.pivot(opts, gathered, world, r)
+            e.pivot(opts, gathered, world, r, lookahead > 0)
+            if lookahead and (it + 1) % lookahead == 0:
+                e.lookahead_flush()
         torch.cuda.synchronize()
+    if lookahead:
+        for e in engs:
+            e.lookahead_flush()
     for r, e in enumerate(engs):
         done, status, n = e.state()
         assert done and status == ref["status"] and n == ref["n_pivots"]
