@@ -216,7 +216,9 @@ def _bench_single_gpu(args):
     s.attach(T.data_ptr(), m, 1, C, ld, n, n + m, keep=T)
     s.generate(args.seed, n, 0)
     torch.cuda.synchronize()
-    opts = native.make_opts(rule=rule, max_pivots=args.pivots, update_variant=variant)
+    # the headline is the rank-1 loop that north_star specifies (one fused tableau pass per pivot): LOOP_GRAPH is set
+    # explicitly because the library's AUTO mode would pick the look-ahead loop for a tableau of this size
+    opts = native.make_opts(rule=rule, max_pivots=args.pivots, update_variant=variant, loop_mode=native.LOOP_GRAPH)
     bytes_per_pivot = 16.0 * R * C
 
     launches = 0

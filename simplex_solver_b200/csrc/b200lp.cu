@@ -629,7 +629,7 @@ static int blk_setup(b200lp_solver* s) {
 }
 
 static int blk_block_size(const b200lp_opts* o) {
-    return o->check_every > 0 ? (int)std::max(1, std::min(BLK_KMAX, o->check_every)) : 8;
+    return o->check_every > 0 ? (int)std::max(1, std::min(BLK_KMAX, o->check_every)) : BLK_KMAX;
 }
 
 static int launch_blk_rowprice(b200lp_solver* s, const b200lp_opts* o, int64_t obj_row, bool sharded) {
@@ -804,7 +804,10 @@ static int run_loop(b200lp_solver* s, const b200lp_opts* o, int64_t obj_row, int
         OnchipPlan plan;
         if (onchip_plan(s, &plan)) return run_onchip(s, o, obj_row, plan, final_state);
     }
-    const int blocked_k = (mode == 0 && o->loop_mode == B200LP_LOOP_BLOCKED && !s->snaps) ? blk_block_size(o) : 0;
+    // AUTO: tableaux beyond L2 (>= 256 MB) take the look-ahead loop -- bit-identical pivots, 1/K of the HBM traffic
+    const bool big = (double)s->R * (double)s->C * 8.0 >= 256.0 * 1024 * 1024;
+    const bool want_blocked = o->loop_mode == B200LP_LOOP_BLOCKED || (o->loop_mode == B200LP_LOOP_AUTO && big);
+    const int blocked_k = (mode == 0 && want_blocked && !s->snaps) ? blk_block_size(o) : 0;
     int iters = o->check_every > 0 ? o->check_every : default_check_every(s);
     if (mode == 1) iters = std::min(iters, 8);
     if (blocked_k) {
