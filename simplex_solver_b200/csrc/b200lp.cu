@@ -1,8 +1,11 @@
 // b200lp.cu -- host side of libb200lp.so: the C ABI of include/b200lp.h over the sm_100a kernels.
 //
-// The pivot loop is device resident: every iteration is three launches (price -> ratio -> update) that
-// communicate through a DevState in device memory; the host replays a CUDA graph of `check_every` iterations
-// and only reads the status word back between replays (double buffered, so the GPU never waits for the host).
+// The pivot loop is device resident; the kernels communicate through a DevState in device memory and the host only
+// reads the status word back between CUDA-graph replays (double buffered, so the GPU never waits for the host).
+// Three drivers (b200lp_opts.loop_mode):
+//   rank-1 graph loop : per pivot [k_pick_cluster (or k_price + k_ratio)] -> k_update_ldg / k_update_tma
+//   on-chip loop      : one persistent cooperative kernel, tableau resident in shared memory (k_solve_onchip)
+//   look-ahead loop   : K x k_pick_cluster<.., BLOCKED> -> k_blk_row -> k_blk_flush  (one tableau pass per K pivots)
 // No cuBLAS, no Triton, no CPU fallback: without a CUDA device every compute entry point fails with
 // B200LP_E_CUDA.
 #include "../../include/b200lp.h"
