@@ -486,7 +486,10 @@ def _bench_sharded(args, rank, local, world):
     opts = native.make_opts(rule=rule, max_pivots=args.pivots)
 
     def make_engine():
-        return CudaShardEngine(m, n_total, rank * ncols, ncols, args.seed, device=local)
+        e = CudaShardEngine(m, n_total, rank * ncols, ncols, args.seed, device=local)
+        if args.exchange == "p2p":  # candidates stored straight into every peer's region over NVLink (no collective)
+            e.enable_p2p(world, rank)
+        return e
 
     eng = make_engine()
     drv = ShardedTableau(eng, world, rank)
@@ -582,7 +585,9 @@ def _bench_sharded(args, rank, local, world):
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": workload_config(args), "roofline": roofline,
             "cpu_baseline": None, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
-            "collective": {"op": "all_gather_into_tensor (NCCL)", "bytes_per_rank_per_pivot": 8 * (R + 2)},
+            "collective": {"op": ("peer-memory push over NVLink (k_p2p_push / k_p2p_pull, torch symmetric memory)"
+                                  if args.exchange == "p2p" else "all_gather_into_tensor (NCCL)"),
+                           "bytes_per_rank_per_pivot": 8 * (R + 2)},
         }
         if lookahead:
             line["lookahead"] = lookahead
@@ -607,6 +612,7 @@ def main():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-secondary", dest="secondary", action="store_false")
     ap.add_argument("--no-lookahead", dest="lookahead", action="store_false")
+    ap.add_argument("--exchange", default="p2p", choices=["p2p", "nccl"], help="per-pivot exchange of the sharded loops")
     args = ap.parse_args()
     world = int(os.environ.get("WORLD_SIZE", "1"))
     if world > 1:

@@ -149,6 +149,10 @@ struct b200lp_solver {
     double* snaps = nullptr;
     int64_t snap_cap = 0;
 
+    // peer-memory exchange of the sharded loops
+    P2PPeers p2p;
+    bool p2p_on = false;
+
     // CTAs per cluster of the single-launch pick kernel (kernels_cluster.cuh); 0 = not available / switched off
     int cluster_ctas = 0;
 
@@ -1346,6 +1350,68 @@ B200LP_API int b200lp_shard_blk_flush(b200lp_solver* s, int64_t obj_row) {
     if (!s || !s->T) return fail(B200LP_E_STATE, "no tableau bound");
     CKR(set_device(s));
     CKR(enqueue_blk_flush(s, BLK_KMAX, obj_row));
+    return 0;
+}
+
+// ---- peer-memory exchange (replaces the caller's all-gather in the sharded loops) ----
+B200LP_API int64_t b200lp_p2p_bytes(int64_t R, int32_t world) {
+    if (R < 1 || world < 1 || world > 16) return -1;
+    return (2 * (int64_t)world * (R + 2) + 2 * (int64_t)world) * 8;
+}
+
+B200LP_API int b200lp_p2p_connect(b200lp_solver* s, void* const* bases, int32_t world, int32_t rank) {
+    if (!s || !s->T) return fail(B200LP_E_STATE, "no tableau bound");
+    if (!bases || world < 1 || world > 16 || rank < 0 || rank >= world) return fail(B200LP_E_INVALID, "bad peer arguments");
+    CKR(set_device(s));
+    memset(&s->p2p, 0, sizeof(s->p2p));
+    for (int g = 0; g < world; ++g) {
+        if (!bases[g]) return fail(B200LP_E_INVALID, "peer %d has no region", g);
+        s->p2p.base[g] = (double*)bases[g];
+    }
+    s->p2p.world = world;
+    s->p2p.rank = rank;
+    s->p2p.xstride = s->R + 2;
+    // own flags start at generation 0 (the caller synchronises all ranks after connect, before the first push)
+    CK(cudaMemsetAsync(s->p2p.base[rank] + 2 * (int64_t)world * s->p2p.xstride, 0, (size_t)2 * world * 8, s->stream));
+    CK(cudaMemsetAsync(&s->st.p->xgen, 0, sizeof(long long), s->stream));
+    CK(cudaMemsetAsync(&s->st.p->ticket_push, 0, sizeof(unsigned int), s->stream));
+    CK(cudaStreamSynchronize(s->stream));
+    s->p2p_on = true;
+    return 0;
+}
+
+// candidate of this shard computed and stored into every peer's region (one kernel after the pricing)
+B200LP_API int b200lp_shard_push(b200lp_solver* s, const b200lp_opts* o, int64_t obj_row, int32_t lookahead) {
+    if (!s || !s->T) return fail(B200LP_E_STATE, "no tableau bound");
+    if (!s->p2p_on) return fail(B200LP_E_STATE, "b200lp_p2p_connect was not called");
+    CKR(check_opts(o));
+    CKR(set_device(s));
+    if (lookahead) CKR(launch_blk_rowprice(s, o, obj_row, true));
+    else CKR(launch_price(s, obj_row, o->rule, o->eps_cost, true));
+    const int blocks = clampi((s->R + BLK_THREADS - 1) / BLK_THREADS, 1, 2 * s->sm_count);
+    if (lookahead) k_p2p_push<true><<<blocks, BLK_THREADS, 0, s->stream>>>(s->T, s->R, s->ld, s->st.p, s->blk, s->p2p);
+    else k_p2p_push<false><<<blocks, BLK_THREADS, 0, s->stream>>>(s->T, s->R, s->ld, s->st.p, s->blk, s->p2p);
+    s->launches++;
+    CK(cudaGetLastError());
+    return 0;
+}
+
+// wait for all candidates of this generation, decide, ratio test (+ rank-1 update unless look-ahead)
+B200LP_API int b200lp_shard_pull(b200lp_solver* s, const b200lp_opts* o, int32_t lookahead) {
+    if (!s || !s->T) return fail(B200LP_E_STATE, "no tableau bound");
+    if (!s->p2p_on) return fail(B200LP_E_STATE, "b200lp_p2p_connect was not called");
+    CKR(check_opts(o));
+    CKR(set_device(s));
+    k_p2p_pull<<<1, 32, 0, s->stream>>>(s->st.p, s->p2p, o->rule == B200LP_RULE_BLAND);
+    s->launches++;
+    CK(cudaGetLastError());
+    const double* ext = s->p2p.base[s->p2p.rank];
+    if (lookahead) {
+        CKR(launch_blk_ratio(s, o, ext, s->p2p.xstride));
+    } else {
+        CKR(launch_ratio(s, o->eps_pivot, false, ext, s->p2p.xstride));
+        CKR(launch_update(s, o->update_variant));
+    }
     return 0;
 }
 

@@ -25,6 +25,9 @@ struct DevState {
     long long max_pivots;
     unsigned int ticket_price;  // last-block-done counters
     unsigned int ticket_ratio;
+    unsigned int ticket_push;   // peer-memory exchange: CTAs of the push kernel that have finished their stores
+    unsigned int pad1;
+    long long xgen;             // peer-memory exchange: generation of the last completed exchange (never reset)
 };
 
 // Candidate of a min-reduction with a total order => the result does not depend on reduction order.

@@ -36,7 +36,8 @@ EXPORTS = [
     "b200lp_shard_candidate", "b200lp_shard_pivot", "b200lp_shard_state", "b200lp_shard_reset",
     "b200lp_read_history", "b200lp_solve_batched", "b200lp_time_update", "b200lp_build_dense",
     "b200lp_set_snapshots", "b200lp_profile_loop", "b200lp_use_own_stream", "b200lp_shard_blk_begin",
-    "b200lp_shard_blk_candidate", "b200lp_shard_blk_pivot", "b200lp_shard_blk_flush",
+    "b200lp_shard_blk_candidate", "b200lp_shard_blk_pivot", "b200lp_shard_blk_flush", "b200lp_p2p_bytes",
+    "b200lp_p2p_connect", "b200lp_shard_push", "b200lp_shard_pull",
 ]
 
 _f64p = C.POINTER(C.c_double)
@@ -130,6 +131,11 @@ def lib():
                 L.b200lp_shard_blk_candidate.argtypes = [C.c_void_p, C.POINTER(Opts), C.c_int64, C.c_void_p]
                 L.b200lp_shard_blk_pivot.argtypes = [C.c_void_p, C.POINTER(Opts), C.c_void_p, C.c_int32, C.c_int32]
                 L.b200lp_shard_blk_flush.argtypes = [C.c_void_p, C.c_int64]
+                L.b200lp_p2p_bytes.restype = C.c_int64
+                L.b200lp_p2p_bytes.argtypes = [C.c_int64, C.c_int32]
+                L.b200lp_p2p_connect.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.c_int32, C.c_int32]
+                L.b200lp_shard_push.argtypes = [C.c_void_p, C.POINTER(Opts), C.c_int64, C.c_int32]
+                L.b200lp_shard_pull.argtypes = [C.c_void_p, C.POINTER(Opts), C.c_int32]
                 L.b200lp_shard_state.argtypes = [C.c_void_p, C.POINTER(C.c_int32), C.POINTER(C.c_int32),
                                                  C.POINTER(C.c_int64)]
                 L.b200lp_shard_reset.argtypes = [C.c_void_p, C.c_int64]
@@ -371,6 +377,20 @@ class Solver:
 
     def shard_blk_flush(self, obj_row: int):
         check(lib().b200lp_shard_blk_flush(self._h, obj_row))
+
+    @staticmethod
+    def p2p_bytes(R: int, world: int) -> int:
+        return int(lib().b200lp_p2p_bytes(R, world))
+
+    def p2p_connect(self, bases, world: int, rank: int):
+        arr = (C.c_void_p * world)(*[C.c_void_p(int(b)) for b in bases])
+        check(lib().b200lp_p2p_connect(self._h, arr, world, rank))
+
+    def shard_push(self, opts: Opts, obj_row: int, lookahead: bool = False):
+        check(lib().b200lp_shard_push(self._h, C.byref(opts), obj_row, 1 if lookahead else 0))
+
+    def shard_pull(self, opts: Opts, lookahead: bool = False):
+        check(lib().b200lp_shard_pull(self._h, C.byref(opts), 1 if lookahead else 0))
 
     def shard_state(self):
         done, status, n = C.c_int32(), C.c_int32(), C.c_int64()

@@ -78,6 +78,33 @@ class CudaShardEngine:
         else:
             self.solver.shard_pivot(opts, gathered.data_ptr(), world, rank)
 
+    # peer-memory exchange (kernels_blocked.cuh: k_p2p_push / k_p2p_pull): candidates are stored straight into every
+    # peer's region over NVLink; no collective call inside the loop
+    def enable_p2p(self, world: int, rank: int, group=None, bases=None, region=None):
+        """Allocate this shard's exchange region in torch symmetric memory, rendezvous, connect.  `bases`/`region` let a
+        single-process test wire two engines by hand."""
+        torch = self.torch
+        n = native.Solver.p2p_bytes(self.R, world) // 8
+        if bases is None:
+            import torch.distributed as dist
+            import torch.distributed._symmetric_memory as symm
+            region = symm.empty(n, dtype=torch.float64, device=f"cuda:{self.device}")
+            hdl = symm.rendezvous(region, group if group is not None else dist.group.WORLD)
+            bases = [int(p) for p in hdl.buffer_ptrs]
+            self._symm = hdl
+        self.region = region
+        self.solver.p2p_connect(bases, world, rank)
+        self.p2p = True
+        if hasattr(self, "_symm"):  # every rank has zeroed its flags before anyone pushes
+            import torch.distributed as dist
+            dist.barrier(group=group)
+
+    def push(self, opts, lookahead: bool = False):
+        self.solver.shard_push(opts, self.m, lookahead)
+
+    def pull(self, opts, lookahead: bool = False):
+        self.solver.shard_pull(opts, lookahead)
+
     # look-ahead loop (kernels_blocked.cuh): pivots are decided from O(R + C) state and applied K at a time
     def lookahead_begin(self):
         self.solver.shard_blk_begin(self.m)
@@ -123,14 +150,19 @@ class ShardedTableau:
 
     def _chunk(self, opts, n, lookahead=0):
         eng = self.engine
+        p2p = getattr(eng, "p2p", False)
         for i in range(n):
-            self._all_gather(eng.candidate(opts, lookahead > 0) if lookahead else eng.candidate(opts))
-            if lookahead:
-                eng.pivot(opts, self.gathered, self.world, self.rank, True)
-                if (i + 1) % lookahead == 0 or i + 1 == n:
-                    eng.lookahead_flush()
+            if p2p:  # push into every peer's region over NVLink, pull from the local one: no collective call
+                eng.push(opts, lookahead > 0)
+                eng.pull(opts, lookahead > 0)
             else:
-                eng.pivot(opts, self.gathered, self.world, self.rank)
+                self._all_gather(eng.candidate(opts, lookahead > 0) if lookahead else eng.candidate(opts))
+                if lookahead:
+                    eng.pivot(opts, self.gathered, self.world, self.rank, True)
+                else:
+                    eng.pivot(opts, self.gathered, self.world, self.rank)
+            if lookahead and ((i + 1) % lookahead == 0 or i + 1 == n):
+                eng.lookahead_flush()
 
     def run(self, opts, max_pivots: int, check_every: int = 0, use_graph: bool = True, lookahead: int = 0):
         """Enqueue pivots until optimal / unbounded / max_pivots.  Returns (status, n_pivots).
@@ -144,13 +176,18 @@ class ShardedTableau:
         """
         eng = self.engine
         eng.reset(max_pivots)
+        if getattr(eng, "p2p", False) and self.world > 1:
+            # the pull kernel gives a missing peer ~9 s before it gives up: start the ranks together
+            import torch.distributed as dist
+            dist.barrier(group=self.group)
         lookahead = int(max(0, min(lookahead, 32)))
         if lookahead:
             eng.lookahead_begin()
         check_every = check_every or max(1, min(max_pivots, 64))
         if lookahead:
             check_every = max(lookahead, check_every // lookahead * lookahead)  # whole blocks per chunk
-        key = (opts.rule, opts.update_variant, opts.eps_cost, opts.eps_pivot, check_every, lookahead)
+        key = (opts.rule, opts.update_variant, opts.eps_cost, opts.eps_pivot, check_every, lookahead,
+               bool(getattr(eng, "p2p", False)))
         graph = self._graphs.get(key) if use_graph else None
         done_total = 0
         while True:

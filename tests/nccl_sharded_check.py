@@ -28,11 +28,14 @@ def main():
     dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
     ok = True
     with torch.cuda.stream(torch.cuda.Stream()):
-        for rule, lookahead in ((native.RULE_BLAND, 0), (native.RULE_DANTZIG, 0), (native.RULE_BLAND, 8),
-                                (native.RULE_DANTZIG, 12)):
+        for rule, lookahead, p2p in ((native.RULE_BLAND, 0, False), (native.RULE_DANTZIG, 0, False),
+                                     (native.RULE_BLAND, 8, False), (native.RULE_DANTZIG, 12, False),
+                                     (native.RULE_BLAND, 0, True), (native.RULE_DANTZIG, 8, True)):
             m, n_total, seed, budget = 384, 1024, 4, 200
             lo, hi = ShardedTableau.columns_of(n_total, world, rank)
             eng = CudaShardEngine(m, n_total, lo, hi - lo, seed, device=local)
+            if p2p:
+                eng.enable_p2p(world, rank)
             drv = ShardedTableau(eng, world, rank)
             opts = native.make_opts(rule=rule, max_pivots=budget)
             status, n = drv.run(opts, budget, check_every=48, lookahead=lookahead)
@@ -47,7 +50,7 @@ def main():
                     and np.array_equal(h["leave_lab"], ref["leave_lab"]) and np.array_equal(rl, one.rowlab)
                     and all(np.array_equal(T[:, j], one.T[:, pos[int(lab)]]) for j, lab in enumerate(cl[:-1]))
                     and np.array_equal(T[:, -1], one.T[:, -1]))
-            print(f"rank {rank} rule {rule} lookahead {lookahead}: status {status} pivots {n} bit-exact vs oracle: {good}", flush=True)
+            print(f"rank {rank} rule {rule} lookahead {lookahead} p2p {p2p}: status {status} pivots {n} bit-exact vs oracle: {good}", flush=True)
             ok = ok and good
             del drv, eng
     flag = torch.tensor([1 if ok else 0], device=f"cuda:{local}")

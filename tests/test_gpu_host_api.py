@@ -157,10 +157,13 @@ def test_cuda_shard_engine_world1_and_emulated_world2(oracle, rule):
     assert_bit_equal(eng.tableau(), one.T, "world-1 shard tableau, look-ahead")
 
     for lookahead in (0, 6):
-        _emulated_two_shards(oracle, one, ref, opts, m, n_total, seed, budget, lookahead)
+        for p2p in (False, True):
+            _emulated_two_shards(oracle, one, ref, opts, m, n_total, seed, budget, lookahead, p2p)
 
 
-def _emulated_two_shards(oracle, one, ref, opts, m, n_total, seed, budget, lookahead):
+def _emulated_two_shards(oracle, one, ref, opts, m, n_total, seed, budget, lookahead, p2p):
+    """Two shards in ONE process on one GPU.  p2p: the peer-memory exchange (push into both regions, pull from the own
+    one) with the regions wired by hand; all pushes are issued before any pull, so no kernel waits for a later one."""
     import torch
     world = 2
     engs = []
@@ -168,17 +171,30 @@ def _emulated_two_shards(oracle, one, ref, opts, m, n_total, seed, budget, looka
         lo, hi = ShardedTableau.columns_of(n_total, world, r)
         engs.append(CudaShardEngine(m, n_total, lo, hi - lo, seed))
     gathered = engs[0].new_buffer(world)
+    if p2p:
+        n = native.Solver.p2p_bytes(m + 1, world) // 8
+        regions = [torch.zeros(n, dtype=torch.float64, device="cuda:0") for _ in range(world)]
+        for r, e in enumerate(engs):
+            e.enable_p2p(world, r, bases=[t.data_ptr() for t in regions], region=regions[r])
     for e in engs:
         e.reset(budget)
         if lookahead:
             e.lookahead_begin()
     stride = m + 1 + 2
     for it in range(budget + 2):
-        for r, e in enumerate(engs):
-            gathered[r * stride:(r + 1) * stride].copy_(e.candidate(opts, lookahead > 0))
-        torch.cuda.synchronize()
-        for r, e in enumerate(engs):
-            e.pivot(opts, gathered, world, r, lookahead > 0)
+        if p2p:
+            for e in engs:
+                e.push(opts, lookahead > 0)
+            torch.cuda.synchronize()
+            for e in engs:
+                e.pull(opts, lookahead > 0)
+        else:
+            for r, e in enumerate(engs):
+                gathered[r * stride:(r + 1) * stride].copy_(e.candidate(opts, lookahead > 0))
+            torch.cuda.synchronize()
+            for r, e in enumerate(engs):
+                e.pivot(opts, gathered, world, r, lookahead > 0)
+        for e in engs:
             if lookahead and (it + 1) % lookahead == 0:
                 e.lookahead_flush()
         torch.cuda.synchronize()
