@@ -33,7 +33,7 @@ class CudaShardEngine:
         import torch
         self.torch = torch
         self.device = device
-        self.m, self.n_total, self.lab0, self.ncols = m, n_total, lab0, ncols
+        self.m, self.n_total, self.lab0, self.ncols, self.seed = m, n_total, lab0, ncols, seed
         self.R, self.C = m + 1, ncols + 1
         self.ld = (self.C + 15) // 16 * 16
         self.T = torch.empty(self.R * self.ld, dtype=torch.float64, device=f"cuda:{device}")
@@ -42,6 +42,10 @@ class CudaShardEngine:
         self.solver.attach(self.T.data_ptr(), m, 1, self.C, self.ld, n_total, n_total + m, keep=self.T)
         self.solver.generate(seed, n_total, lab0)
         self.cand = torch.zeros(self.R + 2, dtype=torch.float64, device=f"cuda:{device}")
+
+    def regenerate(self):
+        """Refill the shard with the synthetic LP it was created with (device-side generator)."""
+        self.solver.generate(self.seed, self.n_total, self.lab0)
 
     def new_buffer(self, world):
         return self.torch.zeros(world * (self.R + 2), dtype=self.torch.float64, device=f"cuda:{self.device}")
