@@ -187,7 +187,7 @@ def workload_config(args):
             "rows": args.rows, "cols": args.cols_total, "rule": args.rule, "pivots_per_step": args.pivots,
             "bytes_per_pivot": 16 * args.rows * args.cols_total,
             "l2": "each shard is far larger than L2", "parallelism": f"column-sharded x{args.gpus}, "
-            "1 all-gather of candidate columns per pivot"}
+            "1 exchange of candidate columns per pivot (see 'collective')"}
 
 
 # ----------------------------------------------------------------------------------------------------------
@@ -485,13 +485,22 @@ def _bench_sharded(args, rank, local, world):
     rule = native.RULE_BLAND if args.rule == "bland" else native.RULE_DANTZIG
     opts = native.make_opts(rule=rule, max_pivots=args.pivots)
 
-    def make_engine():
-        e = CudaShardEngine(m, n_total, rank * ncols, ncols, args.seed, device=local)
-        if args.exchange == "p2p":  # candidates stored straight into every peer's region over NVLink (no collective)
-            e.enable_p2p(world, rank)
-        return e
-
-    eng = make_engine()
+    eng = CudaShardEngine(m, n_total, rank * ncols, ncols, args.seed, device=local)
+    exchange = args.exchange
+    if exchange == "p2p":  # candidates stored straight into every peer's region over NVLink (no collective)
+        # symmetric memory needs peer access between all GPUs of the node; if any rank cannot set it up, every rank
+        # uses the NCCL all-gather exchange instead (same kernels either side of it) and the line says so
+        try:
+            eng.enable_p2p(world, rank)
+            ok = 1
+        except Exception as exc:  # noqa: BLE001
+            print(f"[bench] rank {rank}: peer-memory exchange unavailable ({exc}); using NCCL", file=sys.stderr)
+            ok = 0
+        flag = torch.tensor([ok], dtype=torch.int32, device=f"cuda:{local}")
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        if int(flag.item()) == 0:
+            eng.p2p = False
+            exchange = "nccl"
     drv = ShardedTableau(eng, world, rank)
     torch.cuda.synchronize()
     sampler = ClockSampler(local)
@@ -582,7 +591,7 @@ def _bench_sharded(args, rank, local, world):
             "config": workload_config(args), "roofline": roofline,
             "cpu_baseline": None, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
             "collective": {"op": ("peer-memory push over NVLink (k_p2p_push / k_p2p_pull, torch symmetric memory)"
-                                  if args.exchange == "p2p" else "all_gather_into_tensor (NCCL)"),
+                                  if exchange == "p2p" else "all_gather_into_tensor (NCCL)"),
                            "bytes_per_rank_per_pivot": 8 * (R + 2)},
         }
         if lookahead:

@@ -211,6 +211,8 @@ B200LP_API int b200lp_create(b200lp_solver** out, int device) {
     CK(cudaFuncSetAttribute(k_update_tma<TMA_BOX_R, TMA_STAGES, TMA_STORE_LAG, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                             (int)TmaCfg<TMA_BOX_R, TMA_STAGES>::SMEM_BYTES));
     CK(cudaFuncSetAttribute(k_solve_onchip, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ONCHIP_SMEM_MAX));
+    CK(cudaFuncSetAttribute(k_blk_flush_db<FL_WC, FL_TR, FL_NP>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                            (int)FL_SMEM_BYTES));
     if (!getenv("B200LP_NO_CLUSTER")) {  // diagnostic switch: fall back to the two-launch pick (k_price + k_ratio)
         const void* kernels[4] = {(const void*)k_pick_cluster<false, false>, (const void*)k_pick_cluster<true, false>,
                                   (const void*)k_pick_cluster<false, true>, (const void*)k_pick_cluster<true, true>};
@@ -680,15 +682,15 @@ static int enqueue_blk_flush(b200lp_solver* s, int K, int64_t obj_row) {
     const int wb = clampi((std::max(s->R, s->C) + BLK_THREADS - 1) / BLK_THREADS, 1, 2 * s->sm_count);
     k_blk_row<<<wb, BLK_THREADS, 0, s->stream>>>(s->T, s->R, s->C, s->ld, obj_row, s->st.p, s->blk);
     s->launches++;
-    const int tiles_c = (int)((s->C + 511) / 512);
-    int64_t tr = s->R * tiles_c / ((int64_t)s->sm_count * 8);
-    tr = std::max<int64_t>(8, std::min<int64_t>(BLK_TILE_ROWS, tr / 8 * 8));
-    const int64_t n_tiles = (s->R + tr - 1) / tr * tiles_c;
-    const int grid = clampi(n_tiles, 1, (int64_t)s->sm_count * 16);
-    (void)K;
-    k_blk_flush<<<grid, 256, 0, s->stream>>>(s->T, s->R, s->C, s->ld, s->st.p, s->blk, (int)tr, tiles_c, n_tiles);
+    // pivot rows / pivot column pairs first (general replay), then everything else (plain FMA chains)
+    k_blk_flush_special<<<dim3(FLS_CHUNKS, BLK_KMAX, 2), 256, 0, s->stream>>>(s->T, s->R, s->C, s->ld, s->st.p, s->blk);
+    const int64_t sw = 64 * FL_NP * FL_WC, n_strips = (s->C + sw - 1) / sw, n_rb = (s->R + FL_TR - 1) / FL_TR;
+    const int grid = clampi(n_strips * n_rb, 1, s->sm_count);
+    k_blk_flush_db<FL_WC, FL_TR, FL_NP><<<grid, 256, FL_SMEM_BYTES, s->stream>>>(s->T, s->R, s->C, s->ld, s->st.p,
+                                                                                 s->blk, n_rb, n_strips);
     k_blk_clear<<<1, 1, 0, s->stream>>>(s->st.p, s->blk);
-    s->launches += 2;
+    s->launches += 3;
+    (void)K;
     CK(cudaGetLastError());
     return 0;
 }

@@ -46,6 +46,36 @@ __device__ __forceinline__ double blk_step(double val, bool is_r, bool is_s, dou
     return __fma_rn(-c_i, is_s ? inv_p : q_j, is_s ? 0.0 : val);
 }
 
+// Replay of the t pending steps on ONE element (i, j).  One operand of every step comes from global memory (g[u *
+// gstride]: q_u[j] when G_IS_Q, else col_u[i]), the other from shared memory (sm[u]).  BATCH: the global operands are
+// loaded 8 at a time ahead of the chain so that their L2 latencies overlap -- right for k_blk_flush_special (many CTAs,
+// one element per thread, latency-bound); measured slower in the picks, which are bound by the L2 bandwidth of the 16
+// SMs of the cluster (t * (R + C) * 8 bytes per pick), not by the latency of the individual loads.
+template <bool G_IS_Q, bool BATCH = false>
+__device__ __forceinline__ double blk_replay(double v, int t, const double* __restrict__ g, int64_t gstride,
+                                             const double* sm, const int32_t* sr, const int32_t* ss,
+                                             const double* sinv, int64_t i, int64_t j) {
+    if (BATCH) {
+        for (int u0 = 0; u0 < t; u0 += 8) {
+            double gv[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) gv[k] = (u0 + k < t) ? g[(int64_t)(u0 + k) * gstride] : 0.0;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                const int u = u0 + k;
+                if (u < t)
+                    v = blk_step(v, i == sr[u], j == ss[u], G_IS_Q ? sm[u] : gv[k], G_IS_Q ? gv[k] : sm[u], sinv[u]);
+            }
+        }
+    } else {
+        for (int u = 0; u < t; ++u) {
+            const double gv = g[(int64_t)u * gstride];
+            v = blk_step(v, i == sr[u], j == ss[u], G_IS_Q ? sm[u] : gv, G_IS_Q ? gv : sm[u], sinv[u]);
+        }
+    }
+    return v;
+}
+
 // copy the objective row and the right-hand side out of the stored tableau; no pivots pending
 __global__ void __launch_bounds__(BLK_THREADS)
 k_blk_init(const double* __restrict__ T, int64_t R, int64_t C, int64_t ld, int64_t obj_row, const DevState* st,
@@ -88,8 +118,7 @@ k_blk_ratio(const double* __restrict__ T, int64_t R, int64_t m, int64_t C, int64
             a = src[i];
         } else {
             a = T[i * ld + s];
-            for (int u = 0; u < t; ++u)
-                a = blk_step(a, i == sr[u], s == ss[u], B.colP[(int64_t)u * B.Rpad + i], sq[u], sinv[u]);
+            a = blk_replay<false>(a, t, B.colP + i, B.Rpad, sq, sr, ss, sinv, i, s);
         }
         colT[i] = a;
         if (i < m) {
@@ -183,8 +212,7 @@ k_blk_row(const double* __restrict__ T, int64_t R, int64_t C, int64_t ld, int64_
     const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, nthr = (int64_t)gridDim.x * blockDim.x;
     for (int64_t j = tid; j < C; j += nthr) {
         double v = T[(int64_t)r * ld + j];
-        for (int u = 0; u < t; ++u)
-            v = blk_step(v, r == sr[u], j == ss[u], sc[u], B.qP[(int64_t)u * B.Cpad + j], sinv[u]);
+        v = blk_replay<true>(v, t, B.qP + j, B.Cpad, sc, sr, ss, sinv, r, j);
         const double q = (j == s) ? inv_p : v / p;
         qT[j] = q;
         B.objcur[j] = blk_step(B.objcur[j], false, j == s, c_obj, q, inv_p);
@@ -227,8 +255,7 @@ k_blk_rowprice(const double* __restrict__ T, int64_t R, int64_t C, int64_t ld, i
         const double q_rhs = B.pend->q_rhs;
         for (int64_t j = tid; j < C; j += nthr) {
             double v = T[(int64_t)r * ld + j];
-            for (int u = 0; u < t; ++u)
-                v = blk_step(v, r == sr[u], j == ss[u], sc[u], B.qP[(int64_t)u * B.Cpad + j], sinv[u]);
+            v = blk_replay<true>(v, t, B.qP + j, B.Cpad, sc, sr, ss, sinv, r, j);
             const double q = (j == s) ? inv_p : v / p;
             qT[j] = q;
             const double d = blk_step(B.objcur[j], false, j == s, c_obj, q, inv_p);
@@ -306,109 +333,262 @@ k_blk_rowprice(const double* __restrict__ T, int64_t R, int64_t C, int64_t ld, i
     }
 }
 
-// The flush: every element of the stored tableau replays the pending steps in registers.  Same tiling as
-// k_update_ldg (256 threads x 2 columns x up to 64 rows, streaming 128-bit loads/stores, 8 rows in flight per thread).
-// The steps are taken in chunks of 8: q_u of the chunk for the thread's two columns is (re)loaded into registers per
-// row group (an L1/L2 hit), so the register footprint -- and with it the occupancy that hides the HBM latency -- does
-// not grow with K.  The tile's slice of every col_u is staged in shared memory once per tile (broadcast reads).
-constexpr int BLK_TILE_ROWS = 64;
-constexpr int BLK_UNROLL = 8;
-constexpr int BLK_CHUNK = 8;
+// ---- the flush: k_blk_flush_special + k_blk_flush_db ----------------------------------------------------------------
+// Every element of the stored tableau replays the t pending steps.  Only the elements in a pivot row or a pivot column of
+// a pending step need the general replay (blk_step); there are at most K rows and K columns of them.
+// k_blk_flush_special replays exactly those (pivot rows; pivot columns together with the other column of their 16-byte
+// pair), in place.  k_blk_flush_db replays everything else with the plain chain
+//     v <- fma(-col_u[i], q_u[j], v),  u = 0 .. t-1
+// and neither loads nor stores the special rows / column pairs, so it has no divergent slow path and no tile is slower
+// than the others (with the slow path inside the main kernel, the 12 % of the tiles that hold a pivot row set its
+// duration).  The two kernels touch disjoint elements and an element's replay reads only its own old value, col_u[i] and
+// q_u[j], so their order is free.
+constexpr int FLS_CHUNKS = 64;  // CTAs per pivot row / pivot column pair in the special kernel
 
-__global__ void __launch_bounds__(256, 2)
-k_blk_flush(double* __restrict__ T, int64_t R, int64_t C, int64_t ld, const DevState* st, BlkBuffers B, int tile_rows,
-            int tiles_c, int64_t n_tiles) {
+__global__ void __launch_bounds__(256)
+k_blk_flush_special(double* __restrict__ T, int64_t R, int64_t C, int64_t ld, const DevState* st, BlkBuffers B) {
     __shared__ int32_t sr[BLK_KMAX], ss[BLK_KMAX];
-    __shared__ double sinv[BLK_KMAX];
-    __shared__ __align__(16) double scol[BLK_KMAX][BLK_TILE_ROWS];
+    __shared__ double sinv[BLK_KMAX], sx[BLK_KMAX], sy[BLK_KMAX];
     const int t = (int)(st->n_pivots - B.pend->base);
-    if (t == 0) return;
+    const int u = blockIdx.y, chunk = blockIdx.x;
+    const bool cols = blockIdx.z != 0;
+    if (u >= t) return;
     if (threadIdx.x < t) {
         sr[threadIdx.x] = B.pend->r[threadIdx.x];
         ss[threadIdx.x] = B.pend->s[threadIdx.x];
         sinv[threadIdx.x] = B.pend->inv_p[threadIdx.x];
     }
-    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        const int64_t tc = tile % tiles_c, tr = tile / tiles_c;
-        const int64_t i0 = tr * tile_rows;
-        const int rows = (int)(min(R, i0 + (int64_t)tile_rows) - i0);
-        __syncthreads();  // previous tile's readers are done with scol (and sr/ss/sinv are written)
-        for (int e = threadIdx.x; e < t * rows; e += blockDim.x) {
-            const int u = e / rows, rr = e - u * rows;
-            scol[u][rr] = B.colP[(int64_t)u * B.Rpad + i0 + rr];
+    __syncthreads();
+    if (!cols) {
+        // pivot row of step u (once per distinct row): all columns
+        const int r = sr[u];
+        for (int w = 0; w < u; ++w)
+            if (sr[w] == r) return;
+        if (threadIdx.x < t) sx[threadIdx.x] = B.colP[(int64_t)threadIdx.x * B.Rpad + r];  // col_w[r]
+        __syncthreads();
+        double* row = T + (int64_t)r * ld;
+        for (int64_t j = (int64_t)chunk * blockDim.x + threadIdx.x; j < C; j += (int64_t)FLS_CHUNKS * blockDim.x) {
+            double v = row[j];
+            v = blk_replay<true, true>(v, t, B.qP + j, B.Cpad, sx, sr, ss, sinv, r, j);
+            row[j] = v;
+        }
+    } else {
+        // the 16-byte column pair that holds the pivot column of step u (once per distinct pair): all non-pivot rows
+        const int64_t j0 = ss[u] & ~1;
+        for (int w = 0; w < u; ++w)
+            if ((ss[w] & ~1) == j0) return;
+        const bool two = j0 + 1 < C;
+        if (threadIdx.x < t) {
+            sx[threadIdx.x] = B.qP[(int64_t)threadIdx.x * B.Cpad + j0];
+            sy[threadIdx.x] = two ? B.qP[(int64_t)threadIdx.x * B.Cpad + j0 + 1] : 0.0;
         }
         __syncthreads();
-        const int64_t j = tc * 512 + 2 * threadIdx.x;
-        if (j >= C) continue;
-        unsigned mx = 0, my = 0;  // bit u: this thread's column is s_u
-        bool special_rows = false;
-        for (int u = 0; u < t; ++u) {
-            if (j == ss[u]) mx |= 1u << u;
-            if (j + 1 == ss[u]) my |= 1u << u;
-            special_rows |= (sr[u] >= i0 && sr[u] < i0 + rows);
-        }
-        // does this tile hold a pivot row, or this thread a pivot column?  If not, the replay is t plain FMAs.
-        const bool plain = !special_rows && mx == 0 && my == 0;
-        const double* qbase = B.qP + j;
-        double* base = T + i0 * ld + j;
-        for (int rr = 0; rr < rows; rr += BLK_UNROLL) {
-            double2 v[BLK_UNROLL];
-#pragma unroll
-            for (int w = 0; w < BLK_UNROLL; ++w)
-                if (rr + w < rows) v[w] = ld_stream(reinterpret_cast<const double2*>(base + (int64_t)(rr + w) * ld));
-            for (int u0 = 0; u0 < t; u0 += BLK_CHUNK) {
-                double2 q[BLK_CHUNK];
-#pragma unroll
-                for (int k = 0; k < BLK_CHUNK; ++k)
-                    if (u0 + k < t) q[k] = *reinterpret_cast<const double2*>(qbase + (int64_t)(u0 + k) * B.Cpad);
-                if (plain && u0 + BLK_CHUNK <= t) {
-                    // full chunk, no pivot row / column in sight: 4 x LDS.128 + 16 x DFMA per step for the 8 rows
-                    static_assert(BLK_UNROLL == 8, "the vectorised column reads below assume 8 rows per group");
-#pragma unroll
-                    for (int k = 0; k < BLK_CHUNK; ++k) {
-                        const double2* sc = reinterpret_cast<const double2*>(&scol[u0 + k][rr]);
-                        const double2 c01 = sc[0], c23 = sc[1], c45 = sc[2], c67 = sc[3];
-                        const double c[8] = {c01.x, c01.y, c23.x, c23.y, c45.x, c45.y, c67.x, c67.y};
-#pragma unroll
-                        for (int w = 0; w < BLK_UNROLL; ++w) {
-                            v[w].x = __fma_rn(-c[w], q[k].x, v[w].x);
-                            v[w].y = __fma_rn(-c[w], q[k].y, v[w].y);
-                        }
-                    }
-                } else if (plain) {
-#pragma unroll
-                    for (int k = 0; k < BLK_CHUNK; ++k) {
-                        if (u0 + k < t) {
-#pragma unroll
-                            for (int w = 0; w < BLK_UNROLL; ++w) {
-                                const double nc = -scol[u0 + k][(rr + w) & (BLK_TILE_ROWS - 1)];
-                                v[w].x = __fma_rn(nc, q[k].x, v[w].x);
-                                v[w].y = __fma_rn(nc, q[k].y, v[w].y);
-                            }
-                        }
-                    }
-                } else {
-#pragma unroll
-                    for (int k = 0; k < BLK_CHUNK; ++k) {
-                        if (u0 + k < t) {
-                            const int u = u0 + k;
-#pragma unroll
-                            for (int w = 0; w < BLK_UNROLL; ++w) {
-                                const double c = scol[u][(rr + w) & (BLK_TILE_ROWS - 1)];
-                                const bool is_r = (i0 + rr + w == sr[u]);
-                                v[w].x = blk_step(v[w].x, is_r, (mx >> u) & 1u, c, q[k].x, sinv[u]);
-                                v[w].y = blk_step(v[w].y, is_r, (my >> u) & 1u, c, q[k].y, sinv[u]);
-                            }
-                        }
-                    }
-                }
-            }
-#pragma unroll
-            for (int w = 0; w < BLK_UNROLL; ++w)
-                if (rr + w < rows) st_stream(reinterpret_cast<double2*>(base + (int64_t)(rr + w) * ld), v[w]);
+        for (int64_t i = (int64_t)chunk * blockDim.x + threadIdx.x; i < R; i += (int64_t)FLS_CHUNKS * blockDim.x) {
+            bool pivot_row = false;
+            for (int w = 0; w < t; ++w) pivot_row |= (i == sr[w]);
+            if (pivot_row) continue;  // done by the row part
+            double vx = T[i * ld + j0], vy = two ? T[i * ld + j0 + 1] : 0.0;
+            // (i is not a pivot row: passing -1 as the row keeps blk_replay's row test false)
+            vx = blk_replay<false, true>(vx, t, B.colP + i, B.Rpad, sx, sr, ss, sinv, -1, j0);
+            vy = blk_replay<false, true>(vy, t, B.colP + i, B.Rpad, sy, sr, ss, sinv, -1, j0 + 1);
+            T[i * ld + j0] = vx;
+            if (two) T[i * ld + j0 + 1] = vy;
         }
     }
 }
+
+// Main kernel.  WC warps across by 8 / WC down; tile = TR rows x one strip of SW columns; a CTA takes a contiguous range
+// of tiles in strip-major order, i.e. walks DOWN a strip, so q_u of the strip (SW columns x K steps) is staged in shared
+// memory once per strip and read per step; a warp's row group is 8 rows x its columns, all t steps in registers.
+// Measured on 16384^2 at K = 32 (scripts/probe_flush.py): 2.14 ms for the first version of the flush (tiles of 64 x 512
+// taken grid-stride, q_u re-read per row group through L1 with a 25 % hit rate, slow path per tile) -> 1.10 ms (special
+// kernel + strips + q in shared memory) -> 0.86 ms with the two software pipelines below; what is left is the FP64 pipe
+// (16 us per step = 93 % of its peak) plus the part of the HBM time the replay does not cover.
+//  * tableau rows: a warp issues the loads of its NEXT row group right after step 0 of the current one (registers v /
+//    vn), so the HBM latency is covered by its own replay instead of stalling all warps of the SM in a convoy;
+//  * col_u slices: the next tile's slices are copied global -> shared with cp.async into the other half of a double
+//    buffer while the current tile is replayed; one __syncthreads per tile.
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(smem)), "l"(gmem)
+                 : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
+// NP = 16-byte column pairs per thread (pair p of a lane lies 64 * p columns to the right, so every 128-bit access of a
+// warp is one contiguous 512-byte segment).  NP = 1: 2 CTAs per SM.  NP = 2: a col_u value read from shared memory feeds
+// 4 FMAs instead of 2 -- the shared-memory pipe is the co-bottleneck (72 % of its peak at 45 % FP64 with NP = 1) -- at
+// the price of 128 registers for v and vn alone, hence 1 CTA per SM.
+template <int WC, int TR, int NP>
+__global__ void __launch_bounds__(256, NP == 1 ? 2 : 1)
+k_blk_flush_db(double* __restrict__ T, int64_t R, int64_t C, int64_t ld, const DevState* st, BlkBuffers B, int64_t n_rb,
+               int64_t n_strips) {
+    constexpr int WR = 8 / WC;
+    constexpr int WW = 64 * NP;   // columns per warp
+    constexpr int SW = WW * WC;   // columns per strip
+    constexpr int NG = TR / (8 * WR);
+    static_assert(TR % (8 * WR) == 0 && TR % 2 == 0, "tile rows");
+    __shared__ int32_t sr[BLK_KMAX], ss[BLK_KMAX];
+    extern __shared__ __align__(16) double dyn[];
+    double* scol = dyn;                         // [2][BLK_KMAX][TR]
+    double* sq = dyn + 2 * BLK_KMAX * TR;       // [t][SW]
+    const int t = (int)(st->n_pivots - B.pend->base);
+    if (t == 0) return;
+    if (threadIdx.x < t) {
+        sr[threadIdx.x] = B.pend->r[threadIdx.x];
+        ss[threadIdx.x] = B.pend->s[threadIdx.x];
+    }
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int wc = warp % WC, wr = warp / WC;
+    const int64_t n_items = n_rb * n_strips;
+    const int64_t it0 = n_items * blockIdx.x / gridDim.x, it1 = n_items * (blockIdx.x + 1) / gridDim.x;
+    if (it0 >= it1) return;
+
+    // asynchronous copy of the col_u slices of row block rb into half `buf` (16-byte pieces; Rpad and TR are even)
+    auto stage_cols = [&](int64_t rb, int buf) {
+        const int64_t i0 = rb * TR;
+        const int rows = (int)(min(R, i0 + (int64_t)TR) - i0);
+        const int pieces = (rows + 1) / 2;  // colP is padded to Rpad >= R + (R & 1)
+        double* dst = scol + (int64_t)buf * BLK_KMAX * TR;
+        for (int e = threadIdx.x; e < t * (TR / 2); e += 256) {
+            const int u = e / (TR / 2), pc = e - u * (TR / 2);
+            if (pc < pieces) cp_async16(dst + u * TR + 2 * pc, B.colP + (int64_t)u * B.Rpad + i0 + 2 * pc);
+        }
+        cp_async_commit();
+    };
+
+    // this warp's walk over its row groups: (strip, row block, group) of the group whose loads are issued next
+    int64_t n_strip = it0 / n_rb, n_rbk = it0 - n_strip * n_rb, n_it = it0;
+    int n_g = 0;
+    int64_t skip_strip = -1;
+    bool skip[NP];
+    struct Grp {
+        double* base;
+        unsigned off[NP];  // bit w: do not touch row w of pair p (pivot row / column pair, beyond the tableau)
+    };
+    auto next_group = [&]() {
+        Grp G;
+        const int64_t row0 = n_rbk * TR + (n_g * WR + wr) * 8;
+        const int64_t jj = n_strip * SW + wc * WW + 2 * lane;
+        unsigned off = 0;
+        if (lane < t) {
+            const int64_t d = (int64_t)sr[lane] - row0;
+            if (d >= 0 && d < 8) off = 1u << (int)d;
+        }
+        off = __reduce_or_sync(0xffffffffu, off);
+        if (R - row0 < 8) off |= (R - row0 <= 0) ? 0xffu : (0xffu << (int)(R - row0)) & 0xffu;
+        if (n_strip != skip_strip) {  // a CTA changes strip at most a few times
+            skip_strip = n_strip;
+#pragma unroll
+            for (int p = 0; p < NP; ++p) {
+                skip[p] = jj + 64 * p >= C;
+                for (int u = 0; u < t; ++u) skip[p] |= ((ss[u] & ~1) == jj + 64 * p);
+            }
+        }
+#pragma unroll
+        for (int p = 0; p < NP; ++p) G.off[p] = (n_it >= it1 || skip[p]) ? 0xffu : off;
+        G.base = T + row0 * ld + jj;
+        if (++n_g == NG) {
+            n_g = 0;
+            ++n_it;
+            if (++n_rbk == n_rb) {
+                n_rbk = 0;
+                ++n_strip;
+            }
+        }
+        return G;
+    };
+    auto load = [&](const Grp& G, double2 (*v)[NP]) {
+#pragma unroll
+        for (int w = 0; w < 8; ++w)
+#pragma unroll
+            for (int p = 0; p < NP; ++p) {
+                v[w][p] = make_double2(0.0, 0.0);
+                if (!((G.off[p] >> w) & 1u))
+                    v[w][p] = ld_stream(reinterpret_cast<const double2*>(G.base + (int64_t)w * ld + 64 * p));
+            }
+    };
+
+    double2 vn[8][NP];
+    Grp gn = next_group();
+    load(gn, vn);
+    int64_t strip = it0 / n_rb, rb = it0 - strip * n_rb, cur_strip = -1;
+    stage_cols(rb, 0);
+    for (int64_t it = it0; it < it1; ++it) {
+        const int buf = (int)((it - it0) & 1);
+        cp_async_wait_all();
+        __syncthreads();  // this tile's col_u slices have landed; everybody is done with the previous tile
+        if (strip != cur_strip) {
+            cur_strip = strip;
+            for (int u = warp; u < t; u += 8)
+                for (int c = lane; c < SW; c += 32) {
+                    const int64_t jj = strip * SW + c;
+                    sq[u * SW + c] = jj < B.Cpad ? B.qP[(int64_t)u * B.Cpad + jj] : 0.0;
+                }
+            __syncthreads();
+        }
+        // next tile of this CTA (same strip, next row block, or the top of the next strip)
+        int64_t nstrip = strip, nrb = rb + 1;
+        if (nrb == n_rb) {
+            nrb = 0;
+            ++nstrip;
+        }
+        if (it + 1 < it1) stage_cols(nrb, buf ^ 1);
+        const double* qa = sq + wc * WW + 2 * lane;
+        const double* sc_tile = scol + (int64_t)buf * BLK_KMAX * TR;
+#pragma unroll 1
+        for (int g = 0; g < NG; ++g) {
+            const int rr = (g * WR + wr) * 8;  // rows past the tile's end are masked in `off` and computed on zeros
+            const Grp gc = gn;
+            double2 v[8][NP];
+#pragma unroll
+            for (int w = 0; w < 8; ++w)
+#pragma unroll
+                for (int p = 0; p < NP; ++p) v[w][p] = vn[w][p];
+            auto step = [&](int u) {
+                const double2* sc = reinterpret_cast<const double2*>(sc_tile + u * TR + rr);
+                const double2 c01 = sc[0], c23 = sc[1], c45 = sc[2], c67 = sc[3];
+                const double c[8] = {c01.x, c01.y, c23.x, c23.y, c45.x, c45.y, c67.x, c67.y};
+                double2 q[NP];
+#pragma unroll
+                for (int p = 0; p < NP; ++p) q[p] = *reinterpret_cast<const double2*>(qa + u * SW + 64 * p);
+#pragma unroll
+                for (int w = 0; w < 8; ++w)
+#pragma unroll
+                    for (int p = 0; p < NP; ++p) {
+                        v[w][p].x = __fma_rn(-c[w], q[p].x, v[w][p].x);
+                        v[w][p].y = __fma_rn(-c[w], q[p].y, v[w][p].y);
+                    }
+            };
+            // Step 0 first: it consumes every register of the previous batch of loads, i.e. the wait on their
+            // scoreboard happens HERE, before the same load instructions are issued again for the next group (the
+            // loads of consecutive iterations share one scoreboard, so a wait placed after the re-issue would wait for
+            // the new batch as well and the prefetch would buy nothing).
+            step(0);
+            asm volatile("" ::: "memory");
+            gn = next_group();
+            load(gn, vn);
+            asm volatile("" ::: "memory");
+#pragma unroll 4
+            for (int u = 1; u < t; ++u) step(u);
+#pragma unroll
+            for (int w = 0; w < 8; ++w)
+#pragma unroll
+                for (int p = 0; p < NP; ++p)
+                    if (!((gc.off[p] >> w) & 1u))
+                        st_stream(reinterpret_cast<double2*>(gc.base + (int64_t)w * ld + 64 * p), v[w][p]);
+        }
+        strip = nstrip;
+        rb = nrb;
+    }
+}
+
+// The instance the library launches: 512-column strips, 4 columns per thread, 1 CTA per SM (22.8k pivots/s on 16384^2 at
+// K = 32 against 21.5k for <4, 64, 1> with 2 CTAs per SM).
+constexpr int FL_WC = 4, FL_TR = 128, FL_NP = 2;
+constexpr size_t FL_SMEM_BYTES = (size_t)BLK_KMAX * (64 * FL_NP * FL_WC + 2 * FL_TR) * 8;  // q_u strip + 2 x col_u slices
+static_assert(FL_SMEM_BYTES <= 227 * 1024, "flush shared memory");
 
 // after the flush: nothing pending, and the row part of the block's last pivot has been done by k_blk_row
 __global__ void k_blk_clear(DevState* st, BlkBuffers B) {
@@ -468,8 +648,7 @@ k_p2p_push(const double* __restrict__ T, int64_t R, int64_t ld, DevState* st, Bl
         for (int64_t i = tid; i < R; i += nthr) {
             double a = T[i * ld + s];
             if (LOOKAHEAD)
-                for (int u = 0; u < t; ++u)
-                    a = blk_step(a, i == sr[u], s == ss[u], B.colP[(int64_t)u * B.Rpad + i], sq[u], sinv[u]);
+                a = blk_replay<false>(a, t, B.colP + i, B.Rpad, sq, sr, ss, sinv, i, s);
             for (int g = 0; g < P.world; ++g) P.base[g][slot + 2 + i] = a;
         }
     }
@@ -575,8 +754,7 @@ k_blk_shard_extract(const double* __restrict__ T, int64_t R, int64_t ld, const D
     __syncthreads();
     for (int64_t i = tid; i < R; i += (int64_t)gridDim.x * blockDim.x) {
         double a = T[i * ld + s];
-        for (int u = 0; u < t; ++u)
-            a = blk_step(a, i == sr[u], s == ss[u], B.colP[(int64_t)u * B.Rpad + i], sq[u], sinv[u]);
+        a = blk_replay<false>(a, t, B.colP + i, B.Rpad, sq, sr, ss, sinv, i, s);
         cand[2 + i] = a;
     }
 }

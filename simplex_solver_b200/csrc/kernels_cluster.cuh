@@ -90,8 +90,7 @@ __global__ void __launch_bounds__(CL_THREADS, 1) k_pick_cluster(const PickArgs A
             const double q_rhs = A.B.pend->q_rhs;
             for (int64_t j = gtid; j < C; j += nthr) {
                 double v = A.T[(int64_t)r * ld + j];
-                for (int u = 0; u < t; ++u)
-                    v = blk_step(v, r == sr[u], j == ss[u], sx[u], A.B.qP[(int64_t)u * A.B.Cpad + j], sinv[u]);
+                v = blk_replay<true>(v, t, A.B.qP + j, A.B.Cpad, sx, sr, ss, sinv, r, j);
                 const double q = (j == s) ? inv_p : v / p;
                 qT[j] = q;
                 const double d = blk_step(A.B.objcur[j], false, j == s, c_obj, q, inv_p);
@@ -183,8 +182,7 @@ __global__ void __launch_bounds__(CL_THREADS, 1) k_pick_cluster(const PickArgs A
         double a = __ldcg(A.T + i * ld + s);
         double rhs;
         if (BLOCKED) {
-            for (int u = 0; u < t; ++u)
-                a = blk_step(a, i == sr[u], s == ss[u], A.B.colP[(int64_t)u * A.B.Rpad + i], sx[u], sinv[u]);
+            a = blk_replay<false>(a, t, A.B.colP + i, A.B.Rpad, sx, sr, ss, sinv, i, s);
             rhs = __ldcg(A.B.rhscur + i);
         } else {
             rhs = __ldcg(A.T + i * ld + C - 1);
