@@ -20,6 +20,12 @@ namespace b200lp {
 namespace cg = cooperative_groups;
 
 constexpr int CL_THREADS = 1024;
+// Replay operands loaded 8 at a time ahead of the chain (blk_replay<.., true>): measured SLOWER here (45.3 vs 43.5 us per
+// pivot at K = 32).  The cluster sits in one GPC and its replay traffic, t * (R + C) * 8 bytes per pick, moves at the
+// ~0.6 TB/s of that GPC's path to L2 however many loads are in flight.
+#ifndef PICK_BATCH
+#define PICK_BATCH false
+#endif
 
 struct PickArgs {
     double* T;
@@ -90,7 +96,7 @@ __global__ void __launch_bounds__(CL_THREADS, 1) k_pick_cluster(const PickArgs A
             const double q_rhs = A.B.pend->q_rhs;
             for (int64_t j = gtid; j < C; j += nthr) {
                 double v = A.T[(int64_t)r * ld + j];
-                v = blk_replay<true>(v, t, A.B.qP + j, A.B.Cpad, sx, sr, ss, sinv, r, j);
+                v = blk_replay<true, PICK_BATCH>(v, t, A.B.qP + j, A.B.Cpad, sx, sr, ss, sinv, r, j);
                 const double q = (j == s) ? inv_p : v / p;
                 qT[j] = q;
                 const double d = blk_step(A.B.objcur[j], false, j == s, c_obj, q, inv_p);
@@ -182,7 +188,7 @@ __global__ void __launch_bounds__(CL_THREADS, 1) k_pick_cluster(const PickArgs A
         double a = __ldcg(A.T + i * ld + s);
         double rhs;
         if (BLOCKED) {
-            a = blk_replay<false>(a, t, A.B.colP + i, A.B.Rpad, sx, sr, ss, sinv, i, s);
+            a = blk_replay<false, PICK_BATCH>(a, t, A.B.colP + i, A.B.Rpad, sx, sr, ss, sinv, i, s);
             rhs = __ldcg(A.B.rhscur + i);
         } else {
             rhs = __ldcg(A.T + i * ld + C - 1);
