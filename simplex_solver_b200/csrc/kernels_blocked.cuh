@@ -374,9 +374,10 @@ k_blk_flush_special(double* __restrict__ T, int64_t R, int64_t C, int64_t ld, co
         }
     } else {
         // the 16-byte column pair that holds the pivot column of step u (once per distinct pair): all non-pivot rows
+        if (ss[u] < 0) return;  // sharded tableaux: the entering column of step u lives in another shard
         const int64_t j0 = ss[u] & ~1;
         for (int w = 0; w < u; ++w)
-            if ((ss[w] & ~1) == j0) return;
+            if (ss[w] >= 0 && (ss[w] & ~1) == j0) return;
         const bool two = j0 + 1 < C;
         if (threadIdx.x < t) {
             sx[threadIdx.x] = B.qP[(int64_t)threadIdx.x * B.Cpad + j0];
@@ -483,7 +484,7 @@ k_blk_flush_db(double* __restrict__ T, int64_t R, int64_t C, int64_t ld, const D
 #pragma unroll
             for (int p = 0; p < NP; ++p) {
                 skip[p] = jj + 64 * p >= C;
-                for (int u = 0; u < t; ++u) skip[p] |= ((ss[u] & ~1) == jj + 64 * p);
+                for (int u = 0; u < t; ++u) skip[p] |= (ss[u] >= 0 && (ss[u] & ~1) == jj + 64 * p);
             }
         }
 #pragma unroll
