@@ -176,6 +176,54 @@ def test_device_loop_fixed_budget_bit_exact(solver, oracle, rule, variant):
     assert_bit_equal(got["fun"], ref["fun"], "fun")
 
 
+@pytest.mark.parametrize("shape", [(300, 1100, 0), (700, 520, 3), (129, 513, 1)])
+@pytest.mark.parametrize("K", [5, 32])
+def test_lookahead_ragged_strips_and_row_blocks(solver, oracle, shape, K):
+    """The look-ahead flush walks 512-column strips in 128-row tiles: shapes with several strips / row blocks whose last
+    ones are ragged, an odd number of stored columns, and a row stride with (pad > 0) and without padding."""
+    m, n, pad = shape
+    budget = 70
+    torch = _torch()
+    C = n + 1
+    ld = C + pad + ((C + pad) & 1)
+    T = torch.empty((m + 1) * ld, dtype=torch.float64, device="cuda:0")
+    solver.attach(T.data_ptr(), m, 1, C, ld, n, n + m, keep=T)
+    solver.generate(9, n, 0)
+    for rule in (native.RULE_BLAND, native.RULE_DANTZIG):
+        solver.generate(9, n, 0)
+        got = solver.run(native.make_opts(rule=rule, max_pivots=budget, loop_mode=native.LOOP_BLOCKED, check_every=K),
+                         hist_cap=budget)
+        ot = oracle.OracleTableau.generate(9, m, n)
+        ref = ot.solve(oracle.make_opts(rule=rule, max_pivots=budget), hist_cap=budget)
+        assert got["status"] == ref["status"] and got["n_pivots"] == ref["n_pivots"]
+        np.testing.assert_array_equal(got["piv_row"], ref["piv_row"])
+        np.testing.assert_array_equal(got["piv_col"], ref["piv_col"])
+        assert_bit_equal(solver.read_tableau(), ot.T, f"tableau, rule {rule}")
+
+
+def test_config4_lookahead_equals_rank1_loop_at_full_size(solver):
+    """BASELINE config 4 at full size: 70 Bland pivots through the look-ahead loop (K = 32: two full blocks and a ragged
+    one) leave the 2 GB tableau bit-identical to the rank-1 graph loop's, with the same pivot sequence."""
+    torch = _torch()
+    m = n = 16383
+    T, ld = _device_tableau(solver, m, 1, n + 1, n, n + m)
+    solver.generate(4, n, 0)
+    a = solver.run(native.make_opts(rule=native.RULE_BLAND, max_pivots=70, loop_mode=native.LOOP_GRAPH), hist_cap=70)
+    torch.cuda.synchronize()
+    Ta = T.clone()
+    solver.generate(4, n, 0)
+    b = solver.run(native.make_opts(rule=native.RULE_BLAND, max_pivots=70, loop_mode=native.LOOP_BLOCKED, check_every=32),
+                   hist_cap=70)
+    torch.cuda.synchronize()
+    assert a["n_pivots"] == b["n_pivots"] == 70
+    np.testing.assert_array_equal(a["piv_row"], b["piv_row"])
+    np.testing.assert_array_equal(a["piv_col"], b["piv_col"])
+    assert a["fun"] == b["fun"]
+    # bit patterns, not values: NaN-safe and distinguishes -0.0
+    assert torch.equal(Ta.view(torch.int64), T.view(torch.int64))
+    del T, Ta
+
+
 def test_device_loop_to_optimality(solver, oracle):
     m, n = 96, 160
     T, ld = _device_tableau(solver, m, 1, n + 1, n, n + m)
