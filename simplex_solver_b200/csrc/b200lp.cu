@@ -5,7 +5,8 @@
 // Three drivers (b200lp_opts.loop_mode):
 //   rank-1 graph loop : per pivot [k_pick_cluster (or k_price + k_ratio)] -> k_update_ldg / k_update_tma
 //   on-chip loop      : one persistent cooperative kernel, tableau resident in shared memory (k_solve_onchip)
-//   look-ahead loop   : K x k_pick_cluster<.., BLOCKED> -> k_blk_row -> k_blk_flush  (one tableau pass per K pivots)
+//   look-ahead loop   : K x k_pick_cluster<.., BLOCKED> -> k_blk_row -> k_blk_flush_special + k_blk_flush_db
+//                       (one tableau pass per K pivots)
 // No cuBLAS, no Triton, no CPU fallback: without a CUDA device every compute entry point fails with
 // B200LP_E_CUDA.
 #include "../../include/b200lp.h"
