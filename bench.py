@@ -582,6 +582,11 @@ def _bench_sharded(args, rank, local, world):
            "d2h_bytes_per_step": int(8 * (n_total + 1)),
            "note": "inputs generated on the device inside the timed region: a 137 GB tableau cannot be staged "
                    "through host memory (SURVEY.md 8d); x*, z are read back to the host"}
+    # BASELINE config 3 at N GPUs: the 100k independent 20 x 30 LPs in contiguous blocks per rank (generator blocks of
+    # 1000), one warp per LP, no data-path collective; timed on the device, max over ranks
+    batched = None
+    if args.secondary:
+        batched = bench_batched_sharded(args, rank, local, world, eng.solver)
     launches = args.steps * args.pivots * 5
     if rank == 0:
         line = {
@@ -596,7 +601,66 @@ def _bench_sharded(args, rank, local, world):
         }
         if lookahead:
             line["lookahead"] = lookahead
+        if batched:
+            line["secondary"] = {"config3_batched_20x30": batched}
         print(json.dumps(line))
+
+
+def bench_batched_sharded(args, rank, local, world, solver):
+    import ctypes as C
+    import torch
+    import torch.distributed as dist
+    from simplex_solver_b200 import native
+    from simplex_solver_b200 import workloads as W
+    from simplex_solver_b200.batched import shard_range
+    B = args.batch
+    lo, hi = shard_range(B, world, rank, W.BATCH_BLOCK)
+    k = hi - lo
+    A, b, c, ops = W.batched_small_lps(lo, k)
+    m3, n3 = A.shape[1], A.shape[2]
+    o = native.make_opts()
+    dev = [torch.from_numpy(a).to(f"cuda:{local}") for a in (A, b, c, ops)]
+    dout = [torch.empty(k, dtype=torch.int32, device=f"cuda:{local}"), torch.empty(k, dtype=torch.float64, device=f"cuda:{local}"),
+            torch.empty((k, n3), dtype=torch.float64, device=f"cuda:{local}"), torch.empty(k, dtype=torch.int32, device=f"cuda:{local}")]
+
+    def kernel():
+        return solver.solve_batched_device(k, m3, n3, dev[0].data_ptr(), dev[1].data_ptr(), dev[2].data_ptr(),
+                                           dev[3].data_ptr(), dout[0].data_ptr(), dout[1].data_ptr(), dout[2].data_ptr(),
+                                           dout[3].data_ptr(), o)
+    kernel()
+    torch.cuda.synchronize()
+    dist.barrier()
+    ms = min(kernel() for _ in range(3))
+    pin = [torch.from_numpy(a).pin_memory() for a in (A, b, c, ops)]
+    outs = [torch.empty(k, dtype=torch.int32).pin_memory(), torch.empty(k, dtype=torch.float64).pin_memory(),
+            torch.empty((k, n3), dtype=torch.float64).pin_memory(), torch.empty(k, dtype=torch.int32).pin_memory()]
+    dms = C.c_double()
+
+    def call():
+        native.check(native.lib().b200lp_solve_batched(
+            solver._h, k, m3, n3, C.c_void_p(pin[0].data_ptr()), C.c_void_p(pin[1].data_ptr()),
+            C.c_void_p(pin[2].data_ptr()), C.c_void_p(pin[3].data_ptr()), C.byref(o), C.c_void_p(outs[0].data_ptr()),
+            C.c_void_p(outs[1].data_ptr()), C.c_void_p(outs[2].data_ptr()), C.c_void_p(outs[3].data_ptr()), None, 0, 0,
+            C.byref(dms)))
+    call()
+    walls = []
+    for _ in range(3):
+        torch.cuda.synchronize()
+        dist.barrier()
+        t0 = time.perf_counter()
+        call()
+        walls.append(time.perf_counter() - t0)
+    same = bool((dout[0].cpu().numpy() == outs[0].numpy()).all())
+    t = torch.tensor([ms, min(walls) * 1e3, 0.0 if same else 1.0, float(outs[3].numpy().sum())], dtype=torch.float64,
+                     device=f"cuda:{local}")
+    tmax = t.clone()
+    dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+    dist.all_reduce(t, op=dist.ReduceOp.SUM)
+    kernel_ms, e2e_ms, bad, pivots = float(tmax[0]), float(tmax[1]), float(tmax[2]), float(t[3])
+    return {"batch": B, "per_rank": k, "kernel_ms_max_over_ranks": kernel_ms, "LPs_per_s_kernel": B / (kernel_ms * 1e-3),
+            "pivots_per_s_kernel": pivots / (kernel_ms * 1e-3), "e2e_pinned_ms_max_over_ranks": e2e_ms,
+            "LPs_per_s_e2e_pinned_host": B / (e2e_ms * 1e-3), "device_vs_host_path_status_equal": bad == 0.0,
+            "partition": "contiguous blocks of the batch per rank, no collective in the solve (SURVEY 8e)"}
 
 
 def main():
