@@ -29,6 +29,7 @@
 #include "kernels_cluster.cuh"
 #include "kernels_onchip.cuh"
 #include "kernels_pick.cuh"
+#include "kernels_picks.cuh"
 #include "kernels_update.cuh"
 
 using namespace b200lp;
@@ -156,6 +157,9 @@ struct b200lp_solver {
 
     // CTAs per cluster of the single-launch pick kernel (kernels_cluster.cuh); 0 = not available / switched off
     int cluster_ctas = 0;
+    bool coop_picks = false;        // look-ahead picks: one persistent cooperative kernel per block (kernels_picks.cuh)
+    DevBuf<PickPartB> part_b;
+    DevBuf<int32_t> pk_err;
 
     cudaGraphExec_t graph = nullptr;
     GraphKey graph_key;
@@ -242,6 +246,22 @@ B200LP_API int b200lp_create(b200lp_solver** out, int device) {
         }
     }
     CKR(s->gbar.ensure(1));
+    {   // look-ahead picks as one persistent cooperative kernel (B200LP_NO_COOP_PICKS: diagnostic switch back to one
+        // k_pick_cluster launch per pick)
+        int coop = 0;
+        CK(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, s->device));
+        if (coop && !getenv("B200LP_NO_COOP_PICKS")) {
+            const bool ok = cudaFuncSetAttribute(k_blk_picks<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                 (int)PK_SMEM_MAX) == cudaSuccess &&
+                            cudaFuncSetAttribute(k_blk_picks<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                 (int)PK_SMEM_MAX) == cudaSuccess;
+            cudaGetLastError();
+            s->coop_picks = ok;
+        }
+        CKR(s->part_b.ensure(1024));
+        CKR(s->pk_err.ensure(1));
+        CK(cudaMemsetAsync(s->pk_err.p, 0, sizeof(int32_t), s->stream));
+    }
     CK(cudaStreamSynchronize(s->stream));
     *out = s;
     return 0;
@@ -678,11 +698,60 @@ static int enqueue_blk_pick(b200lp_solver* s, const b200lp_opts* o, int64_t obj_
     return 0;
 }
 
-static int enqueue_blk_flush(b200lp_solver* s, int K, int64_t obj_row) {
-    // the row part of the block's last pivot (the fused kernel would only do it at the next pick)
-    const int wb = clampi((std::max(s->R, s->C) + BLK_THREADS - 1) / BLK_THREADS, 1, 2 * s->sm_count);
-    k_blk_row<<<wb, BLK_THREADS, 0, s->stream>>>(s->T, s->R, s->C, s->ld, obj_row, s->st.p, s->blk);
+// Can the K picks of a block run as ONE cooperative kernel?  Every CTA keeps the history of its C / G columns and
+// R / G rows in shared memory, and all G = #SMs CTAs must be co-resident.
+static bool coop_picks_plan(const b200lp_solver* s, int K, int* wC, int* wR, size_t* smem) {
+    if (!s->coop_picks || s->sm_count > 1024) return false;
+    const int G = s->sm_count;
+    *wC = (int)((s->C + G - 1) / G);
+    *wR = (int)((s->R + G - 1) / G);
+    *smem = (size_t)K * (*wC + *wR) * 8 + (size_t)(*wC + *wR) * 4 + 16;
+    return *smem <= PK_SMEM_MAX;
+}
+
+static int launch_blk_picks(b200lp_solver* s, const b200lp_opts* o, int64_t obj_row, int K, int wC, int wR, size_t smem) {
+    PicksArgs P;
+    P.A.T = s->T;
+    P.A.R = s->R;
+    P.A.m = s->m;
+    P.A.C = s->C;
+    P.A.ld = s->ld;
+    P.A.obj_row = obj_row;
+    P.A.rowlab = s->rowlab.p;
+    P.A.collab = s->collab.p;
+    P.A.art_base = s->art_base;
+    P.A.eps_cost = o->eps_cost;
+    P.A.eps_pivot = o->eps_pivot;
+    P.A.st = s->st.p;
+    P.A.col = s->col.p;
+    P.A.B = s->blk;
+    P.A.h_row = s->h_row.p;
+    P.A.h_col = s->h_col.p;
+    P.A.h_enter = s->h_enter.p;
+    P.A.h_leave = s->h_leave.p;
+    P.A.hist_cap = s->hist_cap;
+    P.K = K;
+    P.wC = wC;
+    P.wR = wR;
+    P.barrier = s->gbar.p;
+    P.partA = s->part_price.p;
+    P.partB = s->part_b.p;
+    P.error = s->pk_err.p;
+    CK(cudaMemsetAsync(s->gbar.p, 0, sizeof(unsigned long long), s->stream));
+    void* args[] = {&P};
+    const void* fn = o->rule == B200LP_RULE_BLAND ? (const void*)k_blk_picks<true> : (const void*)k_blk_picks<false>;
+    CK(cudaLaunchCooperativeKernel(fn, dim3(s->sm_count), dim3(PK_THREADS), args, smem, s->stream));
     s->launches++;
+    return 0;
+}
+
+static int enqueue_blk_flush(b200lp_solver* s, int K, int64_t obj_row, bool row_done = false) {
+    // the row part of the block's last pivot (the fused kernel would only do it at the next pick)
+    if (!row_done) {
+        const int wb = clampi((std::max(s->R, s->C) + BLK_THREADS - 1) / BLK_THREADS, 1, 2 * s->sm_count);
+        k_blk_row<<<wb, BLK_THREADS, 0, s->stream>>>(s->T, s->R, s->C, s->ld, obj_row, s->st.p, s->blk);
+        s->launches++;
+    }
     // pivot rows / pivot column pairs first (general replay), then everything else (plain FMA chains)
     k_blk_flush_special<<<dim3(FLS_CHUNKS, BLK_KMAX, 2), 256, 0, s->stream>>>(s->T, s->R, s->C, s->ld, s->st.p, s->blk);
     const int64_t sw = 64 * FL_NP * FL_WC, n_strips = (s->C + sw - 1) / sw, n_rb = (s->R + FL_TR - 1) / FL_TR;
@@ -697,6 +766,13 @@ static int enqueue_blk_flush(b200lp_solver* s, int K, int64_t obj_row) {
 }
 
 static int enqueue_blk_block(b200lp_solver* s, const b200lp_opts* o, int64_t obj_row, int K) {
+    int wC, wR;
+    size_t smem;
+    if (coop_picks_plan(s, K, &wC, &wR, &smem)) {
+        CKR(launch_blk_picks(s, o, obj_row, K, wC, wR, smem));
+        CKR(enqueue_blk_flush(s, K, obj_row, true));
+        return 0;
+    }
     for (int k = 0; k < K; ++k) CKR(enqueue_blk_pick(s, o, obj_row));
     CKR(enqueue_blk_flush(s, K, obj_row));
     return 0;
@@ -829,10 +905,21 @@ static int run_loop(b200lp_solver* s, const b200lp_opts* o, int64_t obj_row, int
         s->launches++;
         CK(cudaGetLastError());
     }
-    const bool use_graph = o->loop_mode != B200LP_LOOP_LAUNCHES && mode == 0 && s->stream != (cudaStream_t)0;
-    if (use_graph) CKR(get_graph(s, o, obj_row, iters, blocked_k));
+    bool use_graph = o->loop_mode != B200LP_LOOP_LAUNCHES && mode == 0 && s->stream != (cudaStream_t)0;
+    int wC = 0, wR = 0;
+    size_t pk_smem = 0;
+    const bool coop = blocked_k && coop_picks_plan(s, blocked_k, &wC, &wR, &pk_smem);
+    if (use_graph) {
+        const int rc = get_graph(s, o, obj_row, iters, blocked_k);
+        if (rc && coop) {  // a driver that cannot capture a cooperative launch: 4 launches per block need no graph
+            cudaGetLastError();
+            use_graph = false;
+        } else if (rc) {
+            return rc;
+        }
+    }
     const int picks = s->cluster_ctas ? 1 : 2;  // launches per pick
-    const int per_iter = blocked_k ? picks * blocked_k + 3 : picks + 1 + (s->snaps ? 1 : 0);
+    const int per_iter = blocked_k ? (coop ? 4 : picks * blocked_k + 4) : picks + 1 + (s->snaps ? 1 : 0);
     int slot = 0;
     bool first = true;
     for (;;) {
@@ -860,6 +947,15 @@ static int run_loop(b200lp_solver* s, const b200lp_opts* o, int64_t obj_row, int
     // the newest copy is at least as recent as the one that reported done
     const DevState& a = s->st_host[slot];
     *final_state = a.done ? a : s->st_host[slot ^ 1];
+    if (coop && final_state->status == B200LP_STATUS_NUMERICAL) {
+        int32_t err = 0;
+        CK(cudaMemcpy(&err, s->pk_err.p, sizeof(err), cudaMemcpyDeviceToHost));
+        if (err) {
+            CK(cudaMemset(s->pk_err.p, 0, sizeof(err)));
+            return fail(B200LP_E_CUDA, err == 1 ? "look-ahead pick kernel: a grid barrier timed out"
+                                                : "look-ahead pick kernel launched with pivots pending");
+        }
+    }
     return 0;
 }
 
