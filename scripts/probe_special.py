@@ -7,7 +7,7 @@ s = native.Solver(0)
 R = 16384
 T = torch.empty(R * R, dtype=torch.float64, device="cuda:0")
 s.attach(T.data_ptr(), R - 1, 1, R, R, R - 1, 2 * R - 2, keep=T)
-for K in (8, 16, 32):
+for K in [int(x) for x in os.environ.get("PROBE_K", "8,16,32").split(",")]:
     o = dict(loop_mode=native.LOOP_BLOCKED, check_every=K)
     s.generate(4, R - 1, 0)
     s.run(native.make_opts(rule=native.RULE_BLAND, max_pivots=64, **o))

@@ -473,9 +473,9 @@ k_blk_flush_db(double* __restrict__ T, int64_t R, int64_t C, int64_t ld, const D
         const int64_t row0 = n_rbk * TR + (n_g * WR + wr) * 8;
         const int64_t jj = n_strip * SW + wc * WW + 2 * lane;
         unsigned off = 0;
-        if (lane < t) {
-            const int64_t d = (int64_t)sr[lane] - row0;
-            if (d >= 0 && d < 8) off = 1u << (int)d;
+        for (int u = lane; u < t; u += 32) {
+            const int64_t d = (int64_t)sr[u] - row0;
+            if (d >= 0 && d < 8) off |= 1u << (int)d;
         }
         off = __reduce_or_sync(0xffffffffu, off);
         if (R - row0 < 8) off |= (R - row0 <= 0) ? 0xffu : (0xffu << (int)(R - row0)) & 0xffu;
