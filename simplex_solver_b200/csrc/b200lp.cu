@@ -890,9 +890,10 @@ static int run_loop(b200lp_solver* s, const b200lp_opts* o, int64_t obj_row, int
         OnchipPlan plan;
         if (onchip_plan(s, &plan)) return run_onchip(s, o, obj_row, plan, final_state);
     }
-    // AUTO: tableaux beyond L2 (>= 256 MB) take the look-ahead loop -- bit-identical pivots, 1/K of the HBM traffic
-    const bool big = (double)s->R * (double)s->C * 8.0 >= 256.0 * 1024 * 1024;
-    const bool want_blocked = o->loop_mode == B200LP_LOOP_BLOCKED || (o->loop_mode == B200LP_LOOP_AUTO && big);
+    // AUTO: whatever does not fit the on-chip loop takes the look-ahead loop -- bit-identical pivots, one tableau pass
+    // per K pivots.  Measured (scripts/probe_sizes.py, Bland, pivots/s, rank-1 graph loop vs look-ahead K = 32):
+    // 2048^2 53k vs 92k, 4096^2 19k vs 83k, 8192^2 5.7k vs 58k, 16384^2 1.5k vs 25k (on-chip at 1536^2: 120k vs 91k).
+    const bool want_blocked = o->loop_mode == B200LP_LOOP_BLOCKED || o->loop_mode == B200LP_LOOP_AUTO;
     const int blocked_k = (mode == 0 && want_blocked && !s->snaps) ? blk_block_size(o) : 0;
     int iters = o->check_every > 0 ? o->check_every : default_check_every(s);
     if (mode == 1) iters = std::min(iters, 8);

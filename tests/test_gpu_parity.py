@@ -407,6 +407,34 @@ def test_beale_cycling_example_terminates_like_the_oracle(solver, oracle):
     assert_bit_equal(gb["fun"], np.full(5, ref["fun"]), "batched fun")
 
 
+def test_midsize_two_phase_auto_takes_lookahead_and_equals_rank1_loop(solver):
+    """A two-phase LP (<=, >=, = rows) whose tableau (~48 MB) is beyond the on-chip loop: loop_mode AUTO runs it through
+    the look-ahead loop (phase 1, drive-out, phase 2).  Same pivots, same x*, same z* bit for bit as the rank-1 graph
+    loop, which the smaller cases pin against the oracle."""
+    rng = np.random.default_rng(21)
+    m, n = 2000, 3000
+    A = rng.uniform(-1.0, 1.0, (m, n))
+    x0 = rng.random(n)
+    u = rng.random(m)
+    ops = np.where(u < 0.6, 0, np.where(u < 0.85, 1, 2)).astype(np.int8)
+    slack = rng.uniform(0.1, 1.0, m)
+    b = A @ x0 + np.where(ops == 0, slack, np.where(ops == 1, -slack, 0.0))
+    c = rng.uniform(0.1, 1.0, n)
+    cap = 1 << 19  # Dantzig needs ~250k pivots here
+    a = solver.solve_dense(A, b, c, ops, native.make_opts(rule=native.RULE_DANTZIG, loop_mode=native.LOOP_AUTO), hist_cap=cap)
+    g = solver.solve_dense(A, b, c, ops, native.make_opts(rule=native.RULE_DANTZIG, loop_mode=native.LOOP_GRAPH), hist_cap=cap)
+    assert a["status"] == g["status"] == 0
+    assert a["n_pivots"] == g["n_pivots"] and a["n_phase1"] == g["n_phase1"] and a["n_pivots"] < cap
+    np.testing.assert_array_equal(a["piv_row"], g["piv_row"])
+    np.testing.assert_array_equal(a["piv_col"], g["piv_col"])
+    np.testing.assert_array_equal(a["enter_lab"], g["enter_lab"])
+    assert_bit_equal(a["fun"], g["fun"], "fun")
+    assert_bit_equal(a["x"], g["x"], "x")
+    assert np.all(a["x"] >= 0) and np.all(A[ops == 0] @ a["x"] <= b[ops == 0] + 1e-7)
+    assert np.all(A[ops == 1] @ a["x"] >= b[ops == 1] - 1e-7) and np.allclose(A[ops == 2] @ a["x"], b[ops == 2], atol=1e-7)
+    assert a["fun"] <= float(c @ x0) + 1e-9
+
+
 def test_config3_full_size_properties(solver):
     """BASELINE config 3 at full size (100 000 LPs of 20 x 30, two-phase): size-independent properties.
     Status pattern of the generator (index = 0 mod 100 infeasible, = 1 mod 100 unbounded, rest optimal), primal
