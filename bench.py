@@ -317,6 +317,21 @@ def _bench_single_gpu(args):
            "h2d_bytes_per_step": int(8 * (m * n + m + n)),
            "d2h_bytes_per_step": int(8 * (n + 1) + 128), "steps": e2e_steps, "ms_per_step": e2e_sec / e2e_steps * 1e3,
            "call": "b200lp_solve_dense(A, b, c, ops from pinned host memory) -> x, c'x on the host"}
+    if lookahead is not None:
+        # the same host-buffer call with the library's default loop_mode (AUTO -> look-ahead loop at this size)
+        o_auto = native.make_opts(rule=opts.rule, max_pivots=args.pivots)
+        _solve_dense_host_ptr(s2, A_h, b_h, c_h, ops_h, o_auto, m, n, ld)
+        torch.cuda.synchronize()
+        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a0.record()
+        pa = 0
+        for _ in range(e2e_steps):
+            pa += _solve_dense_host_ptr(s2, A_h, b_h, c_h, ops_h, o_auto, m, n, ld)["n_pivots"]
+        a1.record()
+        torch.cuda.synchronize()
+        lookahead["e2e_default_loop_mode"] = {
+            "pivots_per_s": pa / (a0.elapsed_time(a1) * 1e-3), "ms_per_step": a0.elapsed_time(a1) / e2e_steps,
+            "call": "b200lp_solve_dense from pinned host memory with loop_mode = AUTO (the default)"}
     s2.close()
     del Th
     torch.cuda.empty_cache()
