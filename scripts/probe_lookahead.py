@@ -1,4 +1,4 @@
-"""Look-ahead loop pivots/s (K = 32) and a checksum; used to A/B small changes of the pick / flush kernels."""
+"""Look-ahead loop pivots/s (K = 32) and a checksum; used to A/B changes of the pick and flush kernels (PROBE_K=8,16,32)."""
 import os, sys
 sys.path.insert(0, os.path.abspath(os.path.join(os.path.dirname(__file__), "..")))
 import torch

@@ -401,7 +401,7 @@ k_blk_flush_special(double* __restrict__ T, int64_t R, int64_t C, int64_t ld, co
 // Main kernel.  WC warps across by 8 / WC down; tile = TR rows x one strip of SW columns; a CTA takes a contiguous range
 // of tiles in strip-major order, i.e. walks DOWN a strip, so q_u of the strip (SW columns x K steps) is staged in shared
 // memory once per strip and read per step; a warp's row group is 8 rows x its columns, all t steps in registers.
-// Measured on 16384^2 at K = 32 (scripts/probe_flush.py): 2.14 ms for the first version of the flush (tiles of 64 x 512
+// Measured on 16384^2 at K = 32 (scripts/probe_lookahead.py): 2.14 ms for the first version of the flush (tiles of 64 x 512
 // taken grid-stride, q_u re-read per row group through L1 with a 25 % hit rate, slow path per tile) -> 1.10 ms (special
 // kernel + strips + q in shared memory) -> 0.86 ms with the two software pipelines below; what is left is the FP64 pipe
 // (16 us per step = 93 % of its peak) plus the part of the HBM time the replay does not cover.
