@@ -244,3 +244,33 @@ def test_thirty_threads_share_the_library(golden):
         t.join()
     assert not errors, errors[:3]
     assert len(results) == 150 and all(all(r) for r in results)
+
+
+def test_concurrent_cooperative_loops_from_threads():
+    """The on-chip loop and the look-ahead picks are cooperative launches that want every SM.  Six threads, each with its
+    own workspace and stream, run them at the same time: the launches must serialise (not deadlock on each other's grid
+    barriers) and every thread must get the pivots it gets when alone."""
+    import threading
+    A, b, c, ops, mx = W.dense_feasible_lp(160, seed=3)
+    modes = [dict(loop_mode=native.LOOP_BLOCKED, check_every=16), dict(loop_mode=native.LOOP_AUTO),
+             dict(loop_mode=native.LOOP_BLOCKED, check_every=32)]
+    alone = [native.thread_solver(0).solve_dense(A, b, -c, ops, native.make_opts(**mo), hist_cap=4096) for mo in modes]
+    assert alone[0]["n_pivots"] == alone[1]["n_pivots"] == alone[2]["n_pivots"] and alone[0]["status"] == 0
+    errors, same = [], []
+
+    def work(k):
+        try:
+            for rep in range(4):
+                r = native.thread_solver(0).solve_dense(A, b, -c, ops, native.make_opts(**modes[k % 3]), hist_cap=4096)
+                same.append(r["fun"] == alone[0]["fun"] and np.array_equal(r["piv_row"], alone[0]["piv_row"]))
+        except Exception as e:  # noqa: BLE001
+            errors.append(repr(e))
+
+    threads = [threading.Thread(target=work, args=(k,)) for k in range(6)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join(timeout=120)
+    assert not any(t.is_alive() for t in threads), "a thread is stuck"
+    assert not errors, errors[:3]
+    assert len(same) == 24 and all(same)
