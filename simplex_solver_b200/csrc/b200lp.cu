@@ -86,6 +86,10 @@ struct DevBuf {
         p = nullptr;
         cap = 0;
     }
+    DevBuf() = default;
+    DevBuf(const DevBuf&) = delete;
+    DevBuf& operator=(const DevBuf&) = delete;
+    ~DevBuf() { release(); }  // b200lp_destroy deletes the solver: whatever it did not release by name goes here
 };
 
 struct GraphKey {
