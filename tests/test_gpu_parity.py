@@ -211,6 +211,7 @@ def test_config4_lookahead_equals_rank1_loop_at_full_size(solver):
     a = solver.run(native.make_opts(rule=native.RULE_BLAND, max_pivots=70, loop_mode=native.LOOP_GRAPH), hist_cap=70)
     torch.cuda.synchronize()
     Ta = T.clone()
+    torch.cuda.synchronize()  # the copy runs on torch's stream, the generator on the solver's
     solver.generate(4, n, 0)
     b = solver.run(native.make_opts(rule=native.RULE_BLAND, max_pivots=70, loop_mode=native.LOOP_BLOCKED, check_every=32),
                    hist_cap=70)
@@ -258,6 +259,7 @@ def test_config4_full_size_properties(solver):
     p = col[r].item()
     z0 = Tt[m, n].item()
     some = Tt[5:9, 7:11].clone()
+    torch.cuda.synchronize()  # torch's copies above run on torch's stream, the pivot on the solver's
     solver.pivot(r, s, native.UPDATE_AUTO)
     torch.cuda.synchronize()
     inv_p = 1.0 / p
