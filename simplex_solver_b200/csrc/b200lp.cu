@@ -757,7 +757,8 @@ static int enqueue_blk_flush(b200lp_solver* s, int K, int64_t obj_row, bool row_
         s->launches++;
     }
     // pivot rows / pivot column pairs first (general replay), then everything else (plain FMA chains)
-    k_blk_flush_special<<<dim3(FLS_CHUNKS, BLK_KMAX, 2), 256, 0, s->stream>>>(s->T, s->R, s->C, s->ld, s->st.p, s->blk);
+    const unsigned sp_blocks = (unsigned)((std::max(s->R, s->C) + 255) / 256);
+    k_blk_flush_special<<<dim3(sp_blocks, 2), 256, 0, s->stream>>>(s->T, s->R, s->C, s->ld, s->st.p, s->blk);
     const int64_t sw = 64 * FL_NP * FL_WC, n_strips = (s->C + sw - 1) / sw, n_rb = (s->R + FL_TR - 1) / FL_TR;
     const int grid = clampi(n_strips * n_rb, 1, s->sm_count);
     k_blk_flush_db<FL_WC, FL_TR, FL_NP><<<grid, 256, FL_SMEM_BYTES, s->stream>>>(s->T, s->R, s->C, s->ld, s->st.p,

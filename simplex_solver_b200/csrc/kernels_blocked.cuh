@@ -343,55 +343,83 @@ k_blk_rowprice(const double* __restrict__ T, int64_t R, int64_t C, int64_t ld, i
 // than the others (with the slow path inside the main kernel, the 12 % of the tiles that hold a pivot row set its
 // duration).  The two kernels touch disjoint elements and an element's replay reads only its own old value, col_u[i] and
 // q_u[j], so their order is free.
-constexpr int FLS_CHUNKS = 64;  // CTAs per pivot row / pivot column pair in the special kernel
-
+// Thread = one column (row part) or one row (column part): its t history values -- q_u[j] or col_u[i] -- are loaded
+// once into registers and reused for every distinct pivot row / pivot column pair, so the kernel reads the history once
+// (t * (R + C) * 8 bytes) instead of once per pivot row and column.  blockIdx.y: 0 = rows, 1 = column pairs.
 __global__ void __launch_bounds__(256)
 k_blk_flush_special(double* __restrict__ T, int64_t R, int64_t C, int64_t ld, const DevState* st, BlkBuffers B) {
     __shared__ int32_t sr[BLK_KMAX], ss[BLK_KMAX];
-    __shared__ double sinv[BLK_KMAX], sx[BLK_KMAX], sy[BLK_KMAX];
+    __shared__ double sinv[BLK_KMAX];
+    __shared__ int32_t list[BLK_KMAX];               // distinct pivot rows / first columns of the distinct pairs
+    __shared__ int n_list;
+    __shared__ double sm[BLK_KMAX][BLK_KMAX];        // rows: col_u[r_k];  columns: q_u[j0_k]
+    __shared__ double sm2[BLK_KMAX][BLK_KMAX];       // columns: q_u[j0_k + 1]
     const int t = (int)(st->n_pivots - B.pend->base);
-    const int u = blockIdx.y, chunk = blockIdx.x;
-    const bool cols = blockIdx.z != 0;
-    if (u >= t) return;
+    if (t == 0) return;
+    const bool cols = blockIdx.y != 0;
     if (threadIdx.x < t) {
         sr[threadIdx.x] = B.pend->r[threadIdx.x];
         ss[threadIdx.x] = B.pend->s[threadIdx.x];
         sinv[threadIdx.x] = B.pend->inv_p[threadIdx.x];
     }
     __syncthreads();
+    if (threadIdx.x == 0) {
+        int n = 0;
+        for (int u = 0; u < t; ++u) {
+            // (sharded tableaux: ss[u] < 0 when the entering column of step u lives in another shard)
+            const int key = cols ? (ss[u] < 0 ? -1 : (ss[u] & ~1)) : sr[u];
+            bool seen = key < 0;
+            for (int k = 0; k < n && !seen; ++k) seen = list[k] == key;
+            if (!seen) list[n++] = key;
+        }
+        n_list = n;
+    }
+    __syncthreads();
+    const int nl = n_list;
+    if (nl == 0) return;
+    for (int e = threadIdx.x; e < nl * t; e += blockDim.x) {
+        const int k = e / t, u = e - k * t;
+        if (!cols) {
+            sm[k][u] = B.colP[(int64_t)u * B.Rpad + list[k]];
+        } else {
+            sm[k][u] = B.qP[(int64_t)u * B.Cpad + list[k]];
+            sm2[k][u] = B.qP[(int64_t)u * B.Cpad + list[k] + 1];  // (qP is padded past C)
+        }
+    }
+    __syncthreads();
+    const int64_t x = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    double h[BLK_KMAX];  // this thread's history: q_u[j] (rows) or col_u[i] (columns)
     if (!cols) {
-        // pivot row of step u (once per distinct row): all columns
-        const int r = sr[u];
-        for (int w = 0; w < u; ++w)
-            if (sr[w] == r) return;
-        if (threadIdx.x < t) sx[threadIdx.x] = B.colP[(int64_t)threadIdx.x * B.Rpad + r];  // col_w[r]
-        __syncthreads();
-        double* row = T + (int64_t)r * ld;
-        for (int64_t j = (int64_t)chunk * blockDim.x + threadIdx.x; j < C; j += (int64_t)FLS_CHUNKS * blockDim.x) {
-            double v = row[j];
-            v = blk_replay<true, true>(v, t, B.qP + j, B.Cpad, sx, sr, ss, sinv, r, j);
-            row[j] = v;
+        const int64_t j = x;
+        if (j >= C) return;
+#pragma unroll
+        for (int u = 0; u < BLK_KMAX; ++u) h[u] = u < t ? B.qP[(int64_t)u * B.Cpad + j] : 0.0;
+        for (int k = 0; k < nl; ++k) {
+            const int r = list[k];
+            double v = T[(int64_t)r * ld + j];
+#pragma unroll
+            for (int u = 0; u < BLK_KMAX; ++u)
+                if (u < t) v = blk_step(v, r == sr[u], j == ss[u], sm[k][u], h[u], sinv[u]);
+            T[(int64_t)r * ld + j] = v;
         }
     } else {
-        // the 16-byte column pair that holds the pivot column of step u (once per distinct pair): all non-pivot rows
-        if (ss[u] < 0) return;  // sharded tableaux: the entering column of step u lives in another shard
-        const int64_t j0 = ss[u] & ~1;
-        for (int w = 0; w < u; ++w)
-            if (ss[w] >= 0 && (ss[w] & ~1) == j0) return;
-        const bool two = j0 + 1 < C;
-        if (threadIdx.x < t) {
-            sx[threadIdx.x] = B.qP[(int64_t)threadIdx.x * B.Cpad + j0];
-            sy[threadIdx.x] = two ? B.qP[(int64_t)threadIdx.x * B.Cpad + j0 + 1] : 0.0;
-        }
-        __syncthreads();
-        for (int64_t i = (int64_t)chunk * blockDim.x + threadIdx.x; i < R; i += (int64_t)FLS_CHUNKS * blockDim.x) {
-            bool pivot_row = false;
-            for (int w = 0; w < t; ++w) pivot_row |= (i == sr[w]);
-            if (pivot_row) continue;  // done by the row part
+        const int64_t i = x;
+        if (i >= R) return;
+        bool pivot_row = false;
+        for (int u = 0; u < t; ++u) pivot_row |= (i == sr[u]);
+        if (pivot_row) return;  // done by the row part
+#pragma unroll
+        for (int u = 0; u < BLK_KMAX; ++u) h[u] = u < t ? B.colP[(int64_t)u * B.Rpad + i] : 0.0;
+        for (int k = 0; k < nl; ++k) {
+            const int64_t j0 = list[k];
+            const bool two = j0 + 1 < C;
             double vx = T[i * ld + j0], vy = two ? T[i * ld + j0 + 1] : 0.0;
-            // (i is not a pivot row: passing -1 as the row keeps blk_replay's row test false)
-            vx = blk_replay<false, true>(vx, t, B.colP + i, B.Rpad, sx, sr, ss, sinv, -1, j0);
-            vy = blk_replay<false, true>(vy, t, B.colP + i, B.Rpad, sy, sr, ss, sinv, -1, j0 + 1);
+#pragma unroll
+            for (int u = 0; u < BLK_KMAX; ++u)
+                if (u < t) {
+                    vx = blk_step(vx, false, j0 == ss[u], h[u], sm[k][u], sinv[u]);
+                    vy = blk_step(vy, false, j0 + 1 == ss[u], h[u], sm2[k][u], sinv[u]);
+                }
             T[i * ld + j0] = vx;
             if (two) T[i * ld + j0 + 1] = vy;
         }
