@@ -135,6 +135,7 @@ struct b200lp_solver {
     DevBuf<RowInfo> sinfo;
     DevBuf<int8_t> sops;
     DevBuf<int32_t> sstatus, snpiv, slog;
+    DevBuf<unsigned int> snext;  // work counters of the batched launches (one per chunk)
 
     // look-ahead (blocked) loop: pending pivots' columns / rows and the current objective row / right-hand side
     DevBuf<double> blk_colP, blk_qP, blk_obj, blk_rhs;
@@ -1575,12 +1576,22 @@ B200LP_API int b200lp_solve_batched(b200lp_solver* s, int64_t B, int64_t m, int6
     if (warp_bytes > smem_max)
         return fail(B200LP_E_INVALID, "LP of %lld x %lld needs %zu bytes of shared memory per warp; use b200lp_solve_dense",
                     (long long)m, (long long)n, warp_bytes);
-    int wpc = (int)std::min<size_t>(8, smem_max / warp_bytes);
-    // keep several CTAs per SM resident for latency hiding
-    while (wpc > 1 && (size_t)wpc * warp_bytes > 48 * 1024) --wpc;
-    const size_t smem = (size_t)wpc * warp_bytes;
     CK(cudaFuncSetAttribute(k_solve_batched<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max));
     CK(cudaFuncSetAttribute(k_solve_batched<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max));
+    // warps per CTA: the warps are persistent (they draw LPs from a counter), so the CTA size only decides how many warps
+    // fit one SM's shared memory -- take the size with the most resident warps (ties: the larger CTA)
+    int wpc = 1, per_sm = 0, best_warps = 0;
+    for (int cand = 1; cand <= 8 && (size_t)cand * warp_bytes <= smem_max; ++cand) {
+        int occ = 0;
+        if (m + 2 >= 16) CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_solve_batched<4>, cand * 32, (size_t)cand * warp_bytes));
+        else CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_solve_batched<1>, cand * 32, (size_t)cand * warp_bytes));
+        if (occ * cand >= best_warps) {
+            best_warps = occ * cand;
+            wpc = cand;
+            per_sm = occ;
+        }
+    }
+    const size_t smem = (size_t)wpc * warp_bytes;
 
     const double *dA = A, *db = b, *dc = c;
     const int8_t* dops = ops;
@@ -1627,6 +1638,10 @@ B200LP_API int b200lp_solve_batched(b200lp_solver* s, int64_t B, int64_t m, int6
         if (!s->stream2) CK(cudaStreamCreateWithFlags(&s->stream2, cudaStreamNonBlocking));
         q[1] = s->stream2;
     }
+    // persistent warps: one grid of resident CTAs per launch, LPs drawn from a counter
+    const int64_t resident_ctas = (int64_t)std::max(per_sm, 1) * s->sm_count;
+    CKR(s->snext.ensure(8));
+    CK(cudaMemsetAsync(s->snext.p, 0, 8 * sizeof(unsigned int), s->stream));
     CK(cudaEventRecord(s->ev0, s->stream));
     if (nchunk > 1) CK(cudaStreamWaitEvent(s->stream2, s->ev0, 0));
     for (int k = 0; k < nchunk; ++k) {
@@ -1651,7 +1666,8 @@ B200LP_API int b200lp_solve_batched(b200lp_solver* s, int64_t B, int64_t m, int6
         P.x = dx ? dx + lo * n : nullptr;
         P.n_pivots = dnp + lo;
         P.piv_log = dlog ? dlog + lo * log_cap * 2 : nullptr;
-        const int64_t blocks = (nb + wpc - 1) / wpc;
+        P.next = s->snext.p + k;
+        const int64_t blocks = std::min<int64_t>((nb + wpc - 1) / wpc, resident_ctas);
         if (m + 2 >= 16) k_solve_batched<4><<<(unsigned)blocks, wpc * 32, smem, st>>>(P);
         else k_solve_batched<1><<<(unsigned)blocks, wpc * 32, smem, st>>>(P);
         s->launches++;

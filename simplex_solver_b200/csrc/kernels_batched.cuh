@@ -34,6 +34,7 @@ struct BatchedParams {
     int32_t* n_pivots;
     int32_t* piv_log;
     size_t warp_bytes;  // shared memory per warp
+    unsigned int* next;  // work counter of this launch (zeroed by the host)
 };
 
 struct WarpLP {
@@ -44,42 +45,85 @@ struct WarpLP {
     int32_t m, n, R, C, ld, art_base;
 };
 
+// IEEE division whose numerator may be an exact zero (slack / surplus entries, degenerate right-hand sides): a zero
+// numerator sends div.rn.f64 down its slow path (a ~35-instruction subroutine the whole warp waits for; measured at two
+// calls per pivot on the config-3 LPs), so the quotient of a zero is formed as num * den instead -- the same +-0 for
+// every finite non-zero den -- and the divider only ever sees a non-zero numerator.
+__device__ __forceinline__ double div_maybe_zero(double num, double den) {
+    const bool z = (num == 0.0);
+    const double q = (z ? 1.0 : num) / den;
+    return z ? num * den : q;
+}
+
+// The rank-1 update of one lane's columns j (and j + 32 when TWO) over ALL rows, without per-element predicates: row r
+// gets a throw-away value and is overwritten with q right after; column s was zeroed when it was saved, so what the
+// chain loads there is the 0 of the arithmetic contract fma(-col_i, 1/p, 0).  GROUP rows are loaded together before
+// their stores, so the shared-memory latency of one row hides behind the others (a store cannot move above an earlier
+// load of unknown alias); with TWO the broadcast load of col_i, the address arithmetic and the loop control serve two
+// elements.  has1: this lane really owns a column j + 32 (lanes beyond C only skip their accesses).
+template <int GROUP, bool TWO>
+__device__ __forceinline__ void wlp_update_cols(const WarpLP& w, int j, double q0, double q1, bool has1) {
+    double* cell = w.T + j;
+    const double* cb = w.colbuf;
+    const int ld = w.ld;
+    int i = 0;
+    for (; i + GROUP <= w.R; i += GROUP) {
+        double cc[GROUP], t0[GROUP], t1[GROUP];
+#pragma unroll
+        for (int u = 0; u < GROUP; ++u) {
+            cc[u] = cb[u];
+            t0[u] = cell[u * ld];
+            if (TWO) t1[u] = has1 ? cell[u * ld + 32] : 0.0;
+        }
+#pragma unroll
+        for (int u = 0; u < GROUP; ++u) {
+            cell[u * ld] = __fma_rn(-cc[u], q0, t0[u]);
+            if (TWO && has1) cell[u * ld + 32] = __fma_rn(-cc[u], q1, t1[u]);
+        }
+        cell += GROUP * ld;
+        cb += GROUP;
+    }
+    for (; i < w.R; ++i) {
+        const double c0 = cb[0];
+        const double t0 = cell[0];
+        double t1 = 0.0;
+        if (TWO && has1) t1 = cell[32];
+        cell[0] = __fma_rn(-c0, q0, t0);
+        if (TWO && has1) cell[32] = __fma_rn(-c0, q1, t1);
+        cell += ld;
+        ++cb;
+    }
+}
+
 // GROUP: rows whose loads are issued together before their stores (1 = plain loop, fewer registers: better for
 // short tableaux where occupancy matters more; 4 = measured best for the 22-row tableaux of config 3).
 template <int GROUP>
 __device__ __forceinline__ void wlp_pivot(const WarpLP& w, int r, int s, int lane) {
-    for (int i = lane; i < w.R; i += 32) w.colbuf[i] = w.T[i * w.ld + s];
+    // save column s and clear it in place (see wlp_update_cols)
+    for (int i = lane; i < w.R; i += 32) {
+        double* e = w.T + i * w.ld + s;
+        w.colbuf[i] = *e;
+        *e = 0.0;
+    }
     __syncwarp();
     const double p = w.colbuf[r];
     const double inv_p = 1.0 / p;
-    for (int j = lane; j < w.C; j += 32) {
-        const bool is_s = (j == s);
-        const double q = is_s ? inv_p : w.T[r * w.ld + j] / p;
-        // The rank-1 update runs over ALL rows without per-element predicates -- row r gets a throw-away value and is
-        // overwritten with q right after.  All loads of a group are issued before its stores, so the shared-memory
-        // latency of one row hides behind the others (a store cannot move above an earlier load of unknown alias).
-        double* cell = w.T + j;
-        const double* cb = w.colbuf;
-        int i = 0;
-        for (; i + GROUP <= w.R; i += GROUP) {
-            double t[GROUP], cc[GROUP];
-#pragma unroll
-            for (int u = 0; u < GROUP; ++u) {
-                cc[u] = cb[u];
-                t[u] = cell[u * w.ld];
-            }
-#pragma unroll
-            for (int u = 0; u < GROUP; ++u) cell[u * w.ld] = __fma_rn(-cc[u], q, is_s ? 0.0 : t[u]);
-            cell += GROUP * w.ld;
-            cb += GROUP;
+    double* rowr = w.T + r * w.ld;
+    if (w.C > 32) {
+        for (int j = lane; j < w.C; j += 64) {
+            const bool has1 = j + 32 < w.C;
+            const double q0 = (j == s) ? inv_p : div_maybe_zero(rowr[j], p);
+            const double q1 = (j + 32 == s) ? inv_p : div_maybe_zero(has1 ? rowr[j + 32] : 1.0, p);
+            wlp_update_cols<GROUP, true>(w, j, q0, q1, has1);
+            rowr[j] = q0;
+            if (has1) rowr[j + 32] = q1;
         }
-        for (; i < w.R; ++i) {
-            const double t = *cell;
-            *cell = __fma_rn(-cb[0], q, is_s ? 0.0 : t);
-            cell += w.ld;
-            ++cb;
+    } else {
+        if (lane < w.C) {
+            const double q0 = (lane == s) ? inv_p : div_maybe_zero(rowr[lane], p);
+            wlp_update_cols<GROUP, false>(w, lane, q0, 0.0, false);
+            rowr[lane] = q0;
         }
-        w.T[r * w.ld + j] = q;
     }
     __syncwarp();
     if (lane == 0) {
@@ -116,7 +160,7 @@ __device__ __forceinline__ int wlp_ratio(const WarpLP& w, int s, double eps_pivo
         const double a = w.T[i * w.ld + s];
         if (lab >= 0 && a > eps_pivot) {
             Key c;
-            c.v = w.T[i * w.ld + w.C - 1] / a;
+            c.v = div_maybe_zero(w.T[i * w.ld + w.C - 1], a);
             c.lab = lab;
             c.pos = i;
             k = key_min<false>(k, c);
@@ -187,16 +231,12 @@ __device__ __forceinline__ int wlp_drive_out(const WarpLP& w, double eps_pivot, 
     return 0;
 }
 
+// the whole two-phase solve of LP `lp` by one warp in its slice `base` of shared memory
 template <int GROUP>
-__global__ void __launch_bounds__(256) k_solve_batched(const BatchedParams P) {
-    extern __shared__ __align__(16) uint8_t smem_batched[];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpc = blockDim.x >> 5;
-    const int64_t lp = (int64_t)blockIdx.x * wpc + warp;
-    if (lp >= P.B) return;
+__device__ __forceinline__ void wlp_solve_one(const BatchedParams& P, const int64_t lp, uint8_t* base, const int lane) {
     const int m = P.m, n = P.n, ld = P.ld, R = m + 2;
 
     WarpLP w;
-    uint8_t* base = smem_batched + (size_t)warp * P.warp_bytes;
     w.T = reinterpret_cast<double*>(base);
     w.colbuf = w.T + (size_t)R * ld;
     w.rowlab = reinterpret_cast<int32_t*>(w.colbuf + R);
@@ -260,10 +300,12 @@ __global__ void __launch_bounds__(256) k_solve_batched(const BatchedParams P) {
         w.rowlab[m + 1] = -1;
     }
     __syncwarp();
-    for (int e = lane; e < m * n; e += 32) {
-        const int i = e / n, j = e - i * n;
-        const double a = A[e];
-        w.T[i * ld + j] = (w.colbuf[i] < 0.0) ? -a : a;
+    for (int i = 0; i < m; ++i) {
+        const bool flip = w.colbuf[i] < 0.0;  // warp-uniform
+        for (int j = lane; j < n; j += 32) {
+            const double a = A[i * n + j];
+            w.T[i * ld + j] = flip ? -a : a;
+        }
     }
     for (int j = lane; j < n; j += 32) w.T[m * ld + j] = c[j];
     __syncwarp();
@@ -324,6 +366,24 @@ __global__ void __launch_bounds__(256) k_solve_batched(const BatchedParams P) {
         P.status[lp] = st;
         P.fun[lp] = -w.T[m * ld + C - 1];
         P.n_pivots[lp] = run.n_pivots;
+    }
+}
+
+// Persistent warps: the grid is sized to the resident capacity of the chip and every warp draws its next LP from a
+// device counter, so a warp whose LP ends early (infeasible after two pivots, 10 instead of 60 pivots) starts another at
+// once instead of idling until the slowest LP of its CTA has finished.
+template <int GROUP>
+__global__ void __launch_bounds__(256) k_solve_batched(const BatchedParams P) {
+    extern __shared__ __align__(16) uint8_t smem_batched[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint8_t* base = smem_batched + (size_t)warp * P.warp_bytes;
+    for (;;) {
+        unsigned int v = 0;
+        if (lane == 0) v = atomicAdd(P.next, 1u);
+        v = __shfl_sync(0xffffffffu, v, 0);
+        if ((int64_t)v >= P.B) return;
+        wlp_solve_one<GROUP>(P, (int64_t)v, base, lane);
+        __syncwarp();  // the slice is reused by the next LP
     }
 }
 
