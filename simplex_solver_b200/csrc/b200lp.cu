@@ -856,7 +856,7 @@ static bool onchip_plan(const b200lp_solver* s, OnchipPlan* plan) {
 // One phase of the loop as ONE persistent cooperative kernel (kernels_onchip.cuh).
 static int run_onchip(b200lp_solver* s, const b200lp_opts* o, int64_t obj_row, const OnchipPlan& plan, DevState* final_state) {
     CKR(launch_flush(s));
-    const size_t xdoubles = (size_t)2 * plan.G * (s->R + 2);
+    const size_t xdoubles = (size_t)2 * plan.G * onchip_xstride(s->R);
     CKR(s->xbuf.ensure(xdoubles));
     CK(cudaMemsetAsync(s->gbar.p, 0, sizeof(unsigned long long), s->stream));
     OnchipParams P;

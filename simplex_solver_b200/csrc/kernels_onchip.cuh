@@ -18,7 +18,16 @@
 
 namespace b200lp {
 
-constexpr int ONCHIP_THREADS = 256;
+#ifndef B200LP_ONCHIP_THREADS
+#define B200LP_ONCHIP_THREADS 512
+#endif
+constexpr int ONCHIP_THREADS = B200LP_ONCHIP_THREADS;
+constexpr int ONCHIP_WARPS = ONCHIP_THREADS / 32;
+static_assert(3 * ONCHIP_WARPS * 16 <= 1024, "static shared memory of k_solve_onchip exceeds the 1 KB set aside for it");
+constexpr int ONCHIP_CHUNK = 8;  // columns of a row held in registers at once by the update
+// stride of one candidate record [cost, id, column (R doubles)] in the exchange buffer: even, so that the 16-byte
+// header and the column behind it can be read with 128-bit loads
+__host__ __device__ inline int64_t onchip_xstride(int64_t R) { return (R + 3) & ~(int64_t)1; }
 // shared-memory budget: the 227 KB a CTA can opt in to, minus the kernel's static shared memory
 constexpr size_t ONCHIP_SMEM_MAX = 232448 - 1024;
 
@@ -58,10 +67,22 @@ __device__ __forceinline__ void grid_barrier(unsigned long long* counter, unsign
     __syncthreads();
 }
 
+// CTA-wide min of a Key with ONE __syncthreads: every warp reduces the per-warp winners again, so the result is valid in
+// every thread.  `slots` (one Key per warp) must not be reused before another CTA-wide barrier has passed; the kernel
+// gives each of its three reductions its own array.
+template <bool BY_LABEL>
+__device__ __forceinline__ Key block_key_min_all(Key k, Key* slots) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    k = warp_key_min<BY_LABEL>(k);
+    if (lane == 0) slots[warp] = k;
+    __syncthreads();
+    k = lane < ONCHIP_WARPS ? slots[lane] : key_none();
+    return warp_key_min<BY_LABEL>(k);
+}
+
 __global__ void __launch_bounds__(ONCHIP_THREADS, 1) k_solve_onchip(const OnchipParams P) {
     extern __shared__ __align__(16) uint8_t smem_onchip[];
-    __shared__ Key sk[ONCHIP_THREADS / 32];
-    __shared__ Key bc;
+    __shared__ Key sk_price[ONCHIP_WARPS], sk_decide[ONCHIP_WARPS], sk_ratio[ONCHIP_WARPS];
     const int G = gridDim.x, g = blockIdx.x, tid = threadIdx.x;
     const int64_t R = P.R, m = P.m, C = P.C;
     const int stride = P.stride;
@@ -87,7 +108,7 @@ __global__ void __launch_bounds__(ONCHIP_THREADS, 1) k_solve_onchip(const Onchip
     long long n_pivots = P.st->n_pivots;
     const long long max_pivots = P.st->max_pivots;
     int status = -1;
-    const int64_t xstride = R + 2;
+    const int64_t xstride = onchip_xstride(R);
     unsigned long long bar_round = 0;
 
     for (long long it = 0;; ++it) {
@@ -108,10 +129,7 @@ __global__ void __launch_bounds__(ONCHIP_THREADS, 1) k_solve_onchip(const Onchip
                 k = P.rule ? key_min<true>(k, c) : key_min<false>(k, c);
             }
         }
-        k = P.rule ? block_key_min<true>(k, sk) : block_key_min<false>(k, sk);
-        if (tid == 0) bc = k;
-        __syncthreads();
-        const Key mine = bc;
+        const Key mine = P.rule ? block_key_min_all<true>(k, sk_price) : block_key_min_all<false>(k, sk_price);
         // ---- 2. publish the candidate ----
         double* slot = P.xbuf + ((size_t)(it & 1) * G + g) * xstride;
         if (tid == 0) {
@@ -123,47 +141,57 @@ __global__ void __launch_bounds__(ONCHIP_THREADS, 1) k_solve_onchip(const Onchip
         // ---- 3. the grid barrier of this pivot ----
         ++bar_round;
         grid_barrier(P.barrier, bar_round * (unsigned long long)G);
-        // ---- 4. global decision (identical on every CTA) ----
+        // ---- 4. global decision (identical on every CTA): one 16-byte header per candidate ----
         k = key_none();
         const double* xb = P.xbuf + (size_t)(it & 1) * G * xstride;
         for (int b = tid; b < G; b += ONCHIP_THREADS) {
-            const double labd = __ldcg(xb + (size_t)b * xstride + 1);
-            if (labd >= 0.0) {
+            const double2 h = __ldcg(reinterpret_cast<const double2*>(xb + (size_t)b * xstride));
+            if (h.y >= 0.0) {
                 Key c;
-                c.v = __ldcg(xb + (size_t)b * xstride);
-                c.lab = (int32_t)labd;
+                c.v = h.x;
+                c.lab = (int32_t)h.y;
                 c.pos = b;
                 k = P.rule ? key_min<true>(k, c) : key_min<false>(k, c);
             }
         }
-        k = P.rule ? block_key_min<true>(k, sk) : block_key_min<false>(k, sk);
-        if (tid == 0) bc = k;
-        __syncthreads();
-        const Key win = bc;
+        const Key win = P.rule ? block_key_min_all<true>(k, sk_decide) : block_key_min_all<false>(k, sk_decide);
         if (win.lab == B200LP_NO_LAB) {
             status = 0;
             break;
         }
-        const double* wcol = xb + (size_t)win.pos * xstride + 2;
-        for (int64_t i = tid; i < R; i += ONCHIP_THREADS) colbuf[i] = __ldcg(wcol + i);
+        const double2* wcol = reinterpret_cast<const double2*>(xb + (size_t)win.pos * xstride + 2);
+        for (int64_t i2 = tid; 2 * i2 < R; i2 += ONCHIP_THREADS) {
+            const double2 v = __ldcg(wcol + i2);  // the pad element behind an odd R belongs to the record
+            colbuf[2 * i2] = v.x;
+            if (2 * i2 + 1 < R) colbuf[2 * i2 + 1] = v.y;
+        }
         __syncthreads();
-        // ---- ratio test on the RHS replica ----
+        // ---- ratio test on the RHS replica: two rows per trip, so that their divisions overlap ----
         k = key_none();
-        for (int64_t i = tid; i < m; i += ONCHIP_THREADS) {
-            const int32_t lab = rl[i];
-            const double a = colbuf[i];
-            if (lab >= 0 && a > P.eps_pivot) {
+        for (int64_t i0 = tid; i0 < m; i0 += 2 * ONCHIP_THREADS) {
+            const int64_t i1 = i0 + ONCHIP_THREADS;
+            const bool in1 = i1 < m;
+            const int32_t lab0 = rl[i0], lab1 = in1 ? rl[i1] : -1;
+            const double a0 = colbuf[i0], a1 = in1 ? colbuf[i1] : 0.0;
+            const bool ok0 = lab0 >= 0 && a0 > P.eps_pivot, ok1 = lab1 >= 0 && a1 > P.eps_pivot;
+            const double b0 = Tl[i0 * stride + wl], b1 = in1 ? Tl[i1 * stride + wl] : 0.0;
+            const double r0 = b0 / (ok0 ? a0 : 1.0), r1 = b1 / (ok1 ? a1 : 1.0);
+            if (ok0) {
                 Key c;
-                c.v = Tl[i * stride + wl] / a;
-                c.lab = lab;
-                c.pos = (int32_t)i;
+                c.v = r0;
+                c.lab = lab0;
+                c.pos = (int32_t)i0;
+                k = key_min<false>(k, c);
+            }
+            if (ok1) {
+                Key c;
+                c.v = r1;
+                c.lab = lab1;
+                c.pos = (int32_t)i1;
                 k = key_min<false>(k, c);
             }
         }
-        k = block_key_min<false>(k, sk);
-        if (tid == 0) bc = k;
-        __syncthreads();
-        const int r = bc.pos;
+        const int r = block_key_min_all<false>(k, sk_ratio).pos;
         if (r < 0) {
             status = 3;
             break;
@@ -173,18 +201,26 @@ __global__ void __launch_bounds__(ONCHIP_THREADS, 1) k_solve_onchip(const Onchip
         const double inv_p = 1.0 / p;
         for (int j = tid; j <= wl; j += ONCHIP_THREADS) qloc[j] = (j == s_local) ? inv_p : Tl[(int64_t)r * stride + j] / p;
         __syncthreads();
-        // ---- rank-1 update of the local columns (thread = row, odd stride => conflict-free) ----
-        for (int64_t i = tid; i < R; i += ONCHIP_THREADS) {
-            if (i == r) continue;
-            const double nc = -colbuf[i];
-            double* row = Tl + i * stride;
-            for (int j = 0; j <= wl; ++j) {
-                const double t = (j == s_local) ? 0.0 : row[j];
-                row[j] = __fma_rn(nc, qloc[j], t);
+        // ---- rank-1 update of the local columns (thread = row, odd stride => conflict-free).  A chunk of columns is
+        // loaded into registers before anything is stored, so the shared-memory latencies of a row overlap instead of
+        // forming one load -> fma -> store chain per element. ----
+        for (int j0 = 0; j0 <= wl; j0 += ONCHIP_CHUNK) {
+            double q[ONCHIP_CHUNK];
+#pragma unroll
+            for (int u = 0; u < ONCHIP_CHUNK; ++u) q[u] = (j0 + u <= wl) ? qloc[j0 + u] : 0.0;
+            for (int64_t i = tid; i < R; i += ONCHIP_THREADS) {
+                if (i == r) continue;
+                const double nc = -colbuf[i];
+                double* row = Tl + i * stride + j0;
+                double t[ONCHIP_CHUNK];
+#pragma unroll
+                for (int u = 0; u < ONCHIP_CHUNK; ++u) t[u] = (j0 + u <= wl && j0 + u != s_local) ? row[u] : 0.0;
+#pragma unroll
+                for (int u = 0; u < ONCHIP_CHUNK; ++u)
+                    if (j0 + u <= wl) row[u] = __fma_rn(nc, q[u], t[u]);
             }
         }
-        for (int j = tid; j <= wl; j += ONCHIP_THREADS) Tl[(int64_t)r * stride + j] = qloc[j];
-        __syncthreads();
+        for (int j = tid; j <= wl; j += ONCHIP_THREADS) Tl[(int64_t)r * stride + j] = qloc[j];  // row r was skipped above
         // ---- bookkeeping ----
         if (tid == 0) {
             const int32_t leave = rl[r];
