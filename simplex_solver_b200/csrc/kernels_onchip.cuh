@@ -73,8 +73,7 @@ __device__ __forceinline__ void grid_barrier(unsigned long long* counter, unsign
 template <bool BY_LABEL>
 __device__ __forceinline__ Key block_key_min_all(Key k, Key* slots) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    k = warp_key_min<BY_LABEL>(k);
-    if (lane == 0) slots[warp] = k;
+    warp_key_min_store<BY_LABEL>(k, slots + warp);
     __syncthreads();
     k = lane < ONCHIP_WARPS ? slots[lane] : key_none();
     return warp_key_min<BY_LABEL>(k);
@@ -118,7 +117,7 @@ __global__ void __launch_bounds__(ONCHIP_THREADS, 1) k_solve_onchip(const Onchip
         }
         // ---- 1. local pricing ----
         Key k = key_none();
-        for (int j = tid; j < wl; j += ONCHIP_THREADS) {
+        for (int j = wl <= 32 ? (tid & 31) : tid; j < wl; j += ONCHIP_THREADS) {
             const int32_t lab = cl[j];
             const double v = Tl[P.obj_row * stride + j];
             if (lab < P.art_base && v < -P.eps_cost) {
@@ -129,7 +128,9 @@ __global__ void __launch_bounds__(ONCHIP_THREADS, 1) k_solve_onchip(const Onchip
                 k = P.rule ? key_min<true>(k, c) : key_min<false>(k, c);
             }
         }
-        const Key mine = P.rule ? block_key_min_all<true>(k, sk_price) : block_key_min_all<false>(k, sk_price);
+        // (a slice of at most 32 columns is priced by every warp on its own: no shared-memory round trip, no barrier)
+        const Key mine = wl <= 32 ? (P.rule ? warp_key_min<true>(k) : warp_key_min<false>(k))
+                                  : (P.rule ? block_key_min_all<true>(k, sk_price) : block_key_min_all<false>(k, sk_price));
         // ---- 2. publish the candidate ----
         double* slot = P.xbuf + ((size_t)(it & 1) * G + g) * xstride;
         if (tid == 0) {
