@@ -108,18 +108,67 @@ __global__ void __launch_bounds__(ONCHIP_THREADS, 1) k_solve_onchip(const Onchip
     const long long max_pivots = P.st->max_pivots;
     int status = -1;
     const int64_t xstride = onchip_xstride(R);
+    const int64_t obj = P.obj_row;
     unsigned long long bar_round = 0;
+
+    // The update of a pivot is applied in three parts so that most of it runs while the grid barrier of the NEXT pivot is
+    // in flight: (a) the objective row, which is all the next pricing reads; (b) the column that pricing then picks, which
+    // is what gets published; -- arrive at the barrier -- (c) everything else, before the wait.  Every element still
+    // receives exactly one fma with the operands of DESIGN.md section 2, so the bits do not change.
+    bool pending = false;  // colbuf / qloc / pr / ps describe a pivot whose update has not been applied yet
+    int pr = -1, ps = -1;  // its row and, in the CTA that owns the entering column, its local column (else -1)
+
+    // rows of the pending pivot other than row pr and the objective row, columns [0, wl] except `skip`
+    auto update_rest = [&](const int skip) {
+        for (int j0 = 0; j0 <= wl; j0 += ONCHIP_CHUNK) {
+            double q[ONCHIP_CHUNK];
+            bool act[ONCHIP_CHUNK];
+#pragma unroll
+            for (int u = 0; u < ONCHIP_CHUNK; ++u) {
+                act[u] = (j0 + u <= wl) && (j0 + u != skip);
+                q[u] = act[u] ? qloc[j0 + u] : 0.0;
+            }
+            for (int64_t i = tid; i < R; i += ONCHIP_THREADS) {
+                if (i == pr || i == obj) continue;
+                const double nc = -colbuf[i];
+                double* row = Tl + i * stride + j0;
+                double t[ONCHIP_CHUNK];
+#pragma unroll
+                for (int u = 0; u < ONCHIP_CHUNK; ++u) t[u] = (act[u] && j0 + u != ps) ? row[u] : 0.0;
+#pragma unroll
+                for (int u = 0; u < ONCHIP_CHUNK; ++u)
+                    if (act[u]) row[u] = __fma_rn(nc, q[u], t[u]);
+            }
+        }
+        for (int j = tid; j <= wl; j += ONCHIP_THREADS) Tl[(int64_t)pr * stride + j] = qloc[j];  // row pr was skipped above
+    };
+    // the objective row of the pending pivot
+    auto update_obj_row = [&]() {
+        const double nc = -colbuf[obj];
+        for (int j = tid; j <= wl; j += ONCHIP_THREADS) {
+            const double t = (j == ps) ? 0.0 : Tl[obj * stride + j];
+            Tl[obj * stride + j] = __fma_rn(nc, qloc[j], t);
+        }
+    };
 
     for (long long it = 0;; ++it) {
         if (n_pivots >= max_pivots) {
+            if (pending) {
+                update_obj_row();
+                update_rest(-1);
+            }
             status = 1;
             break;
         }
-        // ---- 1. local pricing ----
+        // ---- 1. local pricing on the current objective row ----
+        if (pending) {
+            update_obj_row();
+            __syncthreads();
+        }
         Key k = key_none();
         for (int j = wl <= 32 ? (tid & 31) : tid; j < wl; j += ONCHIP_THREADS) {
             const int32_t lab = cl[j];
-            const double v = Tl[P.obj_row * stride + j];
+            const double v = Tl[obj * stride + j];
             if (lab < P.art_base && v < -P.eps_cost) {
                 Key c;
                 c.v = v;
@@ -131,17 +180,45 @@ __global__ void __launch_bounds__(ONCHIP_THREADS, 1) k_solve_onchip(const Onchip
         // (a slice of at most 32 columns is priced by every warp on its own: no shared-memory round trip, no barrier)
         const Key mine = wl <= 32 ? (P.rule ? warp_key_min<true>(k) : warp_key_min<false>(k))
                                   : (P.rule ? block_key_min_all<true>(k, sk_price) : block_key_min_all<false>(k, sk_price));
-        // ---- 2. publish the candidate ----
+        // ---- 2. publish the candidate (bringing its column up to date on the way) ----
         double* slot = P.xbuf + ((size_t)(it & 1) * G + g) * xstride;
         if (tid == 0) {
             slot[0] = mine.v;
             slot[1] = mine.lab == B200LP_NO_LAB ? -1.0 : (double)mine.lab;
         }
-        if (mine.lab != B200LP_NO_LAB)
-            for (int64_t i = tid; i < R; i += ONCHIP_THREADS) slot[2 + i] = Tl[i * stride + mine.pos];
-        // ---- 3. the grid barrier of this pivot ----
+        const int cand = mine.lab != B200LP_NO_LAB ? mine.pos : -1;
+        if (cand >= 0) {
+            if (pending) {
+                const double qc = qloc[cand];
+                for (int64_t i = tid; i < R; i += ONCHIP_THREADS) {
+                    double* e = Tl + i * stride + cand;
+                    double v;
+                    if (i == pr) v = qc;
+                    else if (i == obj) v = *e;
+                    else v = __fma_rn(-colbuf[i], qc, cand == ps ? 0.0 : *e);
+                    *e = v;
+                    slot[2 + i] = v;
+                }
+            } else {
+                for (int64_t i = tid; i < R; i += ONCHIP_THREADS) slot[2 + i] = Tl[i * stride + cand];
+            }
+        }
+        // ---- 3. the grid barrier of this pivot: arrive, finish the pending update, wait ----
         ++bar_round;
-        grid_barrier(P.barrier, bar_round * (unsigned long long)G);
+        __syncthreads();
+        if (tid == 0) asm volatile("red.release.gpu.global.add.u64 [%0], 1;" ::"l"(P.barrier) : "memory");
+        if (pending) {
+            update_rest(cand);
+            pending = false;
+        }
+        if (tid == 0) {
+            const unsigned long long target = bar_round * (unsigned long long)G;
+            unsigned long long v;
+            do {
+                asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(P.barrier) : "memory");
+            } while (v < target);
+        }
+        __syncthreads();
         // ---- 4. global decision (identical on every CTA): one 16-byte header per candidate ----
         k = key_none();
         const double* xb = P.xbuf + (size_t)(it & 1) * G * xstride;
@@ -197,32 +274,11 @@ __global__ void __launch_bounds__(ONCHIP_THREADS, 1) k_solve_onchip(const Onchip
             status = 3;
             break;
         }
-        const int s_local = (win.pos == g) ? mine.pos : -1;
+        // ---- the pivot is decided: scaled pivot row, labels, history; the update itself stays pending ----
+        const int s_local = (win.pos == g) ? cand : -1;
         const double p = colbuf[r];
         const double inv_p = 1.0 / p;
         for (int j = tid; j <= wl; j += ONCHIP_THREADS) qloc[j] = (j == s_local) ? inv_p : Tl[(int64_t)r * stride + j] / p;
-        __syncthreads();
-        // ---- rank-1 update of the local columns (thread = row, odd stride => conflict-free).  A chunk of columns is
-        // loaded into registers before anything is stored, so the shared-memory latencies of a row overlap instead of
-        // forming one load -> fma -> store chain per element. ----
-        for (int j0 = 0; j0 <= wl; j0 += ONCHIP_CHUNK) {
-            double q[ONCHIP_CHUNK];
-#pragma unroll
-            for (int u = 0; u < ONCHIP_CHUNK; ++u) q[u] = (j0 + u <= wl) ? qloc[j0 + u] : 0.0;
-            for (int64_t i = tid; i < R; i += ONCHIP_THREADS) {
-                if (i == r) continue;
-                const double nc = -colbuf[i];
-                double* row = Tl + i * stride + j0;
-                double t[ONCHIP_CHUNK];
-#pragma unroll
-                for (int u = 0; u < ONCHIP_CHUNK; ++u) t[u] = (j0 + u <= wl && j0 + u != s_local) ? row[u] : 0.0;
-#pragma unroll
-                for (int u = 0; u < ONCHIP_CHUNK; ++u)
-                    if (j0 + u <= wl) row[u] = __fma_rn(nc, q[u], t[u]);
-            }
-        }
-        for (int j = tid; j <= wl; j += ONCHIP_THREADS) Tl[(int64_t)r * stride + j] = qloc[j];  // row r was skipped above
-        // ---- bookkeeping ----
         if (tid == 0) {
             const int32_t leave = rl[r];
             rl[r] = win.lab;
@@ -237,6 +293,9 @@ __global__ void __launch_bounds__(ONCHIP_THREADS, 1) k_solve_onchip(const Onchip
             }
         }
         ++n_pivots;
+        pending = true;
+        pr = r;
+        ps = s_local;
         __syncthreads();
     }
 
