@@ -691,7 +691,8 @@ def main():
     ap.add_argument("--variant", default="auto", choices=["auto", "ldg", "tma"])
     ap.add_argument("--seed", type=int, default=4)
     ap.add_argument("--batch", type=int, default=100000)
-    ap.add_argument("--ref-pivots", type=int, default=32, help="pivots per step of the CPU reference arm")
+    ap.add_argument("--ref-pivots", type=int, default=None,
+                    help="pivots per step of the CPU reference arm (default 32 at N=1, 8 on the config-5 slab)")
     ap.add_argument("--cpu-pivots", type=int, default=384, help="pivots of the cpu_baseline sample")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-secondary", dest="secondary", action="store_false")
@@ -705,10 +706,12 @@ def main():
         args.rows = args.rows or 16384
         args.cols_total = args.rows
         args.pivots = args.pivots or 512
+        args.ref_pivots = args.ref_pivots or 32
     else:
         args.rows = args.rows or 131072
         args.cols_total = args.cols_total or 131072
         args.pivots = args.pivots or 16
+        args.ref_pivots = args.ref_pivots or 8
     if args.impl == "reference":
         run_reference_arm(args)
         return
