@@ -176,6 +176,27 @@ def test_device_loop_fixed_budget_bit_exact(solver, oracle, rule, variant):
     assert_bit_equal(got["fun"], ref["fun"], "fun")
 
 
+@pytest.mark.parametrize("shape", [(40, 6200), (3, 5), (2, 1), (1025, 300), (512, 2047)])
+@pytest.mark.parametrize("rule", [native.RULE_BLAND, native.RULE_DANTZIG])
+def test_onchip_loop_shapes_bit_exact(solver, oracle, rule, shape):
+    """The on-chip persistent loop on the shapes that take its other code paths: slices wider than 32 columns (priced by
+    the whole CTA instead of per warp; 6200 / 148 = 42 columns per SM), fewer columns than SMs, a single column, row counts
+    that leave the last thread of the update / ratio / column-copy loops with a ragged trip."""
+    m, n = shape
+    budget = 90
+    T, ld = _device_tableau(solver, m, 1, n + 1, n, n + m)
+    solver.generate(11, n, 0)
+    got = solver.run(native.make_opts(rule=rule, max_pivots=budget, loop_mode=native.LOOP_AUTO), hist_cap=budget)
+    assert got["kernel_launches"] < 16, "AUTO should have taken the single-launch on-chip loop (plus a few state kernels)"
+    ot = oracle.OracleTableau.generate(11, m, n)
+    ref = ot.solve(oracle.make_opts(rule=rule, max_pivots=budget), hist_cap=budget)
+    assert got["status"] == ref["status"] and got["n_pivots"] == ref["n_pivots"]
+    np.testing.assert_array_equal(got["piv_row"], ref["piv_row"])
+    np.testing.assert_array_equal(got["piv_col"], ref["piv_col"])
+    assert_bit_equal(solver.read_tableau(), ot.T, "tableau")
+    assert_bit_equal(got["fun"], ref["fun"], "fun")
+
+
 @pytest.mark.parametrize("shape", [(300, 1100, 0), (700, 520, 3), (129, 513, 1)])
 @pytest.mark.parametrize("K", [5, 32])
 def test_lookahead_ragged_strips_and_row_blocks(solver, oracle, shape, K):
