@@ -51,7 +51,9 @@ struct WarpLP {
 // every finite non-zero den -- and the divider only ever sees a non-zero numerator.
 __device__ __forceinline__ double div_maybe_zero(double num, double den) {
     const bool z = (num == 0.0);
-    const double q = (z ? 1.0 : num) / den;
+    double safe = z ? 1.0 : num;
+    asm volatile("" : "+d"(safe));  // opaque: otherwise the compiler divides `num` itself and selects afterwards
+    const double q = safe / den;
     return z ? num * den : q;
 }
 
