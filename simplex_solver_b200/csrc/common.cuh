@@ -135,6 +135,19 @@ __device__ __forceinline__ Key block_key_min(Key k, Key* smem) {
     return k;
 }
 
+// CTA-wide min of a Key with ONE __syncthreads, result valid in EVERY thread: the per-warp winners are stored by the
+// lanes that hold them and every warp reduces them again on its own.  For the latency-bound persistent loops, where
+// the two barriers of block_key_min plus a third for a broadcast through shared memory sit on the critical path of a
+// pivot.  `slots` (one Key per warp, at most 32) must not be written again before another CTA-wide barrier has passed:
+// give every call site of a loop its own array.
+template <bool BY_LABEL>
+__device__ __forceinline__ Key block_key_min_all(const Key& k, Key* slots) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = (blockDim.x + 31) >> 5;
+    warp_key_min_store<BY_LABEL>(k, slots + warp);
+    __syncthreads();
+    return warp_key_min<BY_LABEL>(lane < nwarp ? slots[lane] : key_none());
+}
+
 // streaming (evict-first) 128-bit accesses for tableau elements that are touched once per pivot
 __device__ __forceinline__ double2 ld_stream(const double2* p) { return __ldcs(p); }
 __device__ __forceinline__ void st_stream(double2* p, double2 v) { __stcs(p, v); }

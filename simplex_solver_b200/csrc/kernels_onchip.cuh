@@ -67,18 +67,6 @@ __device__ __forceinline__ void grid_barrier(unsigned long long* counter, unsign
     __syncthreads();
 }
 
-// CTA-wide min of a Key with ONE __syncthreads: every warp reduces the per-warp winners again, so the result is valid in
-// every thread.  `slots` (one Key per warp) must not be reused before another CTA-wide barrier has passed; the kernel
-// gives each of its three reductions its own array.
-template <bool BY_LABEL>
-__device__ __forceinline__ Key block_key_min_all(Key k, Key* slots) {
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    warp_key_min_store<BY_LABEL>(k, slots + warp);
-    __syncthreads();
-    k = lane < ONCHIP_WARPS ? slots[lane] : key_none();
-    return warp_key_min<BY_LABEL>(k);
-}
-
 __global__ void __launch_bounds__(ONCHIP_THREADS, 1) k_solve_onchip(const OnchipParams P) {
     extern __shared__ __align__(16) uint8_t smem_onchip[];
     __shared__ Key sk_price[ONCHIP_WARPS], sk_decide[ONCHIP_WARPS], sk_ratio[ONCHIP_WARPS];

@@ -62,8 +62,7 @@ __global__ void __launch_bounds__(PK_THREADS, 1) k_blk_picks(const PicksArgs P) 
     extern __shared__ __align__(16) double dyn_pk[];
     __shared__ int32_t sr[BLK_KMAX], ss[BLK_KMAX];
     __shared__ double sinv[BLK_KMAX], sx[BLK_KMAX];
-    __shared__ Key sk[PK_THREADS / 32];
-    __shared__ Key bcK;
+    __shared__ Key skA[PK_THREADS / 32], skW[PK_THREADS / 32], skB[PK_THREADS / 32], skV[PK_THREADS / 32];  // one per reduction
     __shared__ PickPartB bcB;
     const PickArgs& A = P.A;
     DevState* st = A.st;
@@ -153,7 +152,7 @@ __global__ void __launch_bounds__(PK_THREADS, 1) k_blk_picks(const PicksArgs P) 
             }
         }
         pend = false;
-        k = block_key_min<BLAND>(k, sk);
+        k = block_key_min_all<BLAND>(k, skA);
         if (tid == 0) P.partA[g] = k;
         ok = grid_barrier_wd(P.barrier, ++round * (unsigned long long)G);
         if (!ok) break;
@@ -166,10 +165,7 @@ __global__ void __launch_bounds__(PK_THREADS, 1) k_blk_picks(const PicksArgs P) 
             c.pos = (int32_t)(__double_as_longlong(raw.y) >> 32);
             w = key_min<BLAND>(w, c);
         }
-        w = block_key_min<BLAND>(w, sk);
-        if (tid == 0) bcK = w;
-        __syncthreads();
-        const Key win = bcK;
+        const Key win = block_key_min_all<BLAND>(w, skW);
         if (n_piv >= max_pivots || win.lab == B200LP_NO_LAB) {
             status = n_piv >= max_pivots ? 1 : 0;  // LIMIT is checked first, as in the oracle
             no_candidate = win.lab == B200LP_NO_LAB;
@@ -203,10 +199,9 @@ __global__ void __launch_bounds__(PK_THREADS, 1) k_blk_picks(const PicksArgs P) 
             }
         }
         {
-            const Key wb = block_key_min<false>(kb, sk);
+            const Key wb = block_key_min_all<false>(kb, skB);
             if (tid == 0) bcB.k = wb;
-            __syncthreads();
-            if (bcB.k.lab != B200LP_NO_LAB && kb.lab != B200LP_NO_LAB && kb.pos == bcB.k.pos) {
+            if (wb.lab != B200LP_NO_LAB && kb.lab != B200LP_NO_LAB && kb.pos == wb.pos) {  // the one thread that holds it
                 bcB.a = ka;
                 bcB.rhs = krhs;
             }
@@ -229,10 +224,9 @@ __global__ void __launch_bounds__(PK_THREADS, 1) k_blk_picks(const PicksArgs P) 
             }
         }
         {
-            const Key wb = block_key_min<false>(kb, sk);
+            const Key wb = block_key_min_all<false>(kb, skV);
             if (tid == 0) bcB.k = wb;
-            __syncthreads();
-            if (bcB.k.lab != B200LP_NO_LAB && kb.lab != B200LP_NO_LAB && kb.pos == bcB.k.pos) {
+            if (wb.lab != B200LP_NO_LAB && kb.lab != B200LP_NO_LAB && kb.pos == wb.pos) {
                 bcB.a = ka;
                 bcB.rhs = krhs;
             }
