@@ -1561,6 +1561,7 @@ B200LP_API int b200lp_solve_batched(b200lp_solver* s, int64_t B, int64_t m, int6
     CKR(check_opts(o));
     if (B < 0 || m < 0 || n < 1) return fail(B200LP_E_INVALID, "bad batch shape B=%lld m=%lld n=%lld", (long long)B, (long long)m, (long long)n);
     if (B == 0) return 0;
+    if (B > 0x7fffffff) return fail(B200LP_E_INVALID, "batch of %lld LPs: split it (the work counter of a launch is 32 bits wide)", (long long)B);
     if (!A && m > 0) return fail(B200LP_E_INVALID, "A is NULL");
     if (!c || (m > 0 && (!b || !ops)) || !status || !fun || !n_pivots) return fail(B200LP_E_INVALID, "NULL argument");
     CKR(set_device(s));
