@@ -1,7 +1,7 @@
 // kernels_onchip.cuh -- the pivot loop for tableaux that fit the chip's aggregate shared memory (~30 MB):
 // one persistent cooperative kernel, the tableau column-sharded over the SMs and RESIDENT IN SHARED MEMORY for the
 // whole phase, ONE grid barrier per pivot.  This is the path of BASELINE config 2 (1024 x 1024, 8.4 MB), which is
-// latency-bound, not HBM-bound: the multi-kernel loop costs 12-16 us per pivot there, this loop ~7 us.
+// latency-bound, not HBM-bound: the multi-kernel loop costs 12-16 us per pivot there, this loop 4.7 us.
 //
 // Layout (the multi-GPU column sharding of sharded.py, applied across SMs): CTA g owns columns [lo_g, hi_g) of EVERY
 // row plus its own replica of the right-hand-side column and of the row labels.  Per pivot:
