@@ -91,6 +91,10 @@ def lib():
         L.orc_solve_batched.argtypes = [C.c_int64, C.c_int64, C.c_int64, _f64p, _f64p, _f64p, _i8p,
                                         C.POINTER(Opts), _i32p, _f64p, _f64p, _i32p, _i32p, C.c_int64, C.c_int32]
         L.orc_max_threads.restype = C.c_int
+        _i64p = C.POINTER(C.c_int64)
+        L.orc_full_dims.argtypes = [_f64p, _i8p, C.c_int64, C.c_int64, _i64p, _i64p]
+        L.orc_full_steps.argtypes = [_f64p, C.c_int64, _f64p, _f64p, _i8p, C.c_int64, C.c_int64, C.POINTER(Opts),
+                                     C.c_int64, _f64p, _i32p, _i32p, _i32p, _i32p, _i64p]
         _lib = L
     return _lib
 
@@ -242,6 +246,38 @@ def solve_batched(A, b, c, ops, opts=None, log_cap=0, threads=1):
                             _p(status, _i32p), _p(fun, _f64p), _p(x, _f64p), _p(npiv, _i32p),
                             _p(log, _i32p) if log is not None else None, log_cap, threads)
     return {"status": status, "fun": fun, "x": x, "n_pivots": npiv, "piv_log": log}
+
+
+def full_steps(A, b, c, ops, opts=None, cap=64):
+    """Textbook FULL-tableau simplex (orc_full_steps): the displayed tableau of every step, as `pivotSteps` shows it.
+
+    Returns dict(status, n_pivots, n_phase1, var_ids, basis, steps) with steps[k] = (tableau R x W, pivot row,
+    pivot column index in the displayed tableau); steps[0] is the initial tableau with (None, None)."""
+    opts = opts or make_opts()
+    A = np.ascontiguousarray(A, dtype=np.float64)
+    b = np.ascontiguousarray(b, dtype=np.float64)
+    c = np.ascontiguousarray(c, dtype=np.float64)
+    ops = np.ascontiguousarray(ops, dtype=np.int8)
+    m, n = len(b), len(c)
+    R, W = C.c_int64(), C.c_int64()
+    lib().orc_full_dims(_p(b, _f64p), _p(ops, _i8p), m, n, C.byref(R), C.byref(W))
+    R, W = int(R.value), int(W.value)
+    snaps = np.zeros((cap + 1, R, W), dtype=np.float64)
+    pr = np.full(max(cap, 1), -1, dtype=np.int32)
+    pc = np.full(max(cap, 1), -1, dtype=np.int32)
+    var_ids = np.zeros(max(W - 1, 1), dtype=np.int32)
+    basis = np.zeros(max(m, 1), dtype=np.int32)
+    out = np.zeros(6, dtype=np.int64)
+    rc = lib().orc_full_steps(_p(A, _f64p), max(n, 1), _p(b, _f64p), _p(c, _f64p), _p(ops, _i8p), m, n, C.byref(opts),
+                              cap, _p(snaps, _f64p), _p(pr, _i32p), _p(pc, _i32p), _p(var_ids, _i32p),
+                              _p(basis, _i32p), out.ctypes.data_as(C.POINTER(C.c_int64)))
+    if rc:
+        raise MemoryError("orc_full_steps")
+    n_piv = int(out[2])
+    k = min(n_piv, cap)
+    steps = [(snaps[0], None, None)] + [(snaps[i + 1], int(pr[i]), int(pc[i])) for i in range(k)]
+    return {"status": int(out[3]), "n_pivots": n_piv, "n_phase1": int(out[4]), "var_ids": var_ids[: W - 1].copy(),
+            "basis": basis[:m].copy(), "steps": steps, "truncated": n_piv > cap}
 
 
 def max_threads():

@@ -17,7 +17,7 @@
  *
  * Pinning.  Status / z* / x* are pinned against golden vectors produced in the build container by the
  * reference's own SolverController.run() with real scipy HiGHS (tests/golden/make_golden.py ->
- * tests/golden/*.json; checked by tests/test_oracle_golden.py).  The PIVOT SEQUENCE and tableau entries are
+ * tests/golden/reference_golden.json; checked by tests/test_oracle_golden.py).  The PIVOT SEQUENCE and tableau entries are
  * "parity unpinned": no reference test or fixture holds a single tableau cell or pivot index
  * (SURVEY.md F4), so for those this file is the definition the CUDA path is compared with bit-for-bit.
  *
@@ -434,6 +434,259 @@ ORC_EXPORT int orc_solve_batched(int64_t B, int64_t m, int64_t n, const double *
             free(hr);
         }
     }
+    return 0;
+}
+
+/* ---- textbook FULL-tableau two-phase simplex (pivotSteps checker) ------------------------------------------
+ * An independent restatement of the same algorithm on the tableau as a user sees it -- the layout of
+ * step["tableau"] consumed at solver_controller.py:332-362 (and printed by pdf_report_service.py:135-177): EVERY
+ * variable owns an explicit column, ordered by variable id (structural x1..xn, then the slack / surplus variable of
+ * each inequality row, then the artificial of each >= / = row), then the right-hand side; basic columns are carried
+ * as unit vectors and updated like any other column.  No label arrays, no condensed storage: "lowest variable id" is
+ * simply "lowest column index".  It shares nothing with the condensed code above but the arithmetic contract (one
+ * division per pivot-row element, one fma per other element) and the decision rules, so that it can check both the
+ * condensed oracle and the GPU's pivotSteps bit for bit:
+ *   q_j = T[r][j] / p  gives 1 at the entering column and 1/p at the leaving variable's (unit) column;
+ *   fma(-col_i, q_j, T[i][j]) gives exactly 0 at the entering column, leaves other unit columns alone
+ *   (q_j = 0) and gives fma(-col_i, 1/p, 0) at the leaving variable's column -- the condensed update rules.
+ * snaps receives (cap + 1) tableaux of R x W doubles: step 0 = the initial tableau, step k = after pivot k.
+ * out[0..5] = R, W, pivots done, status, pivots in phase 1 (+ drive-out), art_base.                           */
+typedef struct {
+    int64_t m, R, W, n_real; /* n_real: columns [0, n_real) are not artificial */
+    double *T;
+    int32_t *basis;          /* column index basic in row i; -1 - index when the row is flagged redundant */
+    int32_t *is_basic;       /* per column */
+} orc_full;
+
+static int64_t orcf_price(const orc_full *f, int64_t obj_row, int32_t rule, double eps_cost) {
+    const double *d = f->T + obj_row * f->W;
+    int64_t best = -1;
+    for (int64_t j = 0; j < f->n_real; ++j) {
+        if (f->is_basic[j]) continue;
+        if (!(d[j] < -eps_cost)) continue;
+        if (best < 0) best = j;
+        else if (rule != ORC_RULE_BLAND && d[j] < d[best]) best = j; /* ties and Bland: the lower index stays */
+    }
+    return best;
+}
+
+static int64_t orcf_ratio(const orc_full *f, int64_t s, double eps_pivot) {
+    int64_t best = -1;
+    double best_ratio = 0.0;
+    for (int64_t i = 0; i < f->m; ++i) {
+        if (f->basis[i] < 0) continue;
+        double a = f->T[i * f->W + s];
+        if (!(a > eps_pivot)) continue;
+        double ratio = f->T[i * f->W + f->W - 1] / a;
+        if (best < 0 || ratio < best_ratio || (ratio == best_ratio && f->basis[i] < f->basis[best])) {
+            best = i;
+            best_ratio = ratio;
+        }
+    }
+    return best;
+}
+
+static void orcf_pivot(orc_full *f, int64_t r, int64_t s) {
+    const int64_t R = f->R, W = f->W;
+    double *rowr = f->T + r * W;
+    const double p = rowr[s];
+    double *col = (double *)malloc((size_t)R * sizeof(double));
+    for (int64_t i = 0; i < R; ++i) col[i] = f->T[i * W + s];
+    for (int64_t j = 0; j < W; ++j) rowr[j] = rowr[j] / p;
+    for (int64_t i = 0; i < R; ++i) {
+        if (i == r) continue;
+        double *row = f->T + i * W;
+        const double nc = -col[i];
+        for (int64_t j = 0; j < W; ++j) row[j] = __builtin_fma(nc, rowr[j], row[j]);
+    }
+    free(col);
+    f->is_basic[f->basis[r]] = 0;
+    f->is_basic[s] = 1;
+    f->basis[r] = (int32_t)s;
+}
+
+typedef struct {
+    int64_t n_pivots, cap;
+    double *snaps;
+    int32_t *piv_row, *piv_col;
+} orcf_log;
+
+static void orcf_record(const orc_full *f, orcf_log *L, int64_t r, int64_t s) {
+    if (L->n_pivots < L->cap) {
+        L->piv_row[L->n_pivots] = (int32_t)r;
+        L->piv_col[L->n_pivots] = (int32_t)s;
+        memcpy(L->snaps + (L->n_pivots + 1) * f->R * f->W, f->T, (size_t)(f->R * f->W) * sizeof(double));
+    }
+    L->n_pivots++;
+}
+
+static int orcf_phase(orc_full *f, int64_t obj_row, int32_t rule, const orc_opts *o, int64_t max_pivots, orcf_log *L) {
+    for (;;) {
+        if (L->n_pivots >= max_pivots) return ORC_LIMIT;
+        int64_t s = orcf_price(f, obj_row, rule, o->eps_cost);
+        if (s < 0) return ORC_OPT;
+        int64_t r = orcf_ratio(f, s, o->eps_pivot);
+        if (r < 0) return ORC_UNBOUNDED;
+        orcf_pivot(f, r, s);
+        orcf_record(f, L, r, s);
+    }
+}
+
+ORC_EXPORT int orc_full_dims(const double *b, const int8_t *ops, int64_t m, int64_t n, int64_t *R, int64_t *W) {
+    int64_t n_log = 0, n_art = 0;
+    for (int64_t i = 0; i < m; ++i) {
+        int op = ops[i];
+        if (b[i] < 0.0 && op != ORC_EQ) op = (op == ORC_LE) ? ORC_GE : ORC_LE;
+        if (op != ORC_EQ) ++n_log;
+        if (op != ORC_LE) ++n_art;
+    }
+    *R = m + (n_art > 0 ? 2 : 1);
+    *W = n + n_log + n_art + 1;
+    return 0;
+}
+
+ORC_EXPORT int orc_full_steps(const double *A, int64_t lda, const double *b, const double *c, const int8_t *ops,
+                              int64_t m, int64_t n, const orc_opts *o, int64_t cap, double *snaps, int32_t *piv_row,
+                              int32_t *piv_col, int32_t *var_ids, int32_t *basis_out, int64_t *out) {
+    orc_full f;
+    int64_t R, W;
+    orc_full_dims(b, ops, m, n, &R, &W);
+    f.m = m;
+    f.R = R;
+    f.W = W;
+    f.T = (double *)calloc((size_t)(R * W), sizeof(double));
+    f.basis = (int32_t *)calloc((size_t)(m > 0 ? m : 1), sizeof(int32_t));
+    f.is_basic = (int32_t *)calloc((size_t)W, sizeof(int32_t));
+    int32_t *logcol = (int32_t *)malloc((size_t)(m > 0 ? m : 1) * sizeof(int32_t));
+    int32_t *artcol = (int32_t *)malloc((size_t)(m > 0 ? m : 1) * sizeof(int32_t));
+    if (!f.T || !f.basis || !f.is_basic || !logcol || !artcol) return -1;
+    const int32_t art_base = (int32_t)(n + m);
+    /* columns in variable-id order */
+    int64_t k = n, n_ge = 0;
+    for (int64_t j = 0; j < n; ++j) var_ids[j] = (int32_t)j;
+    for (int64_t i = 0; i < m; ++i) {
+        int op = ops[i];
+        if (b[i] < 0.0 && op != ORC_EQ) op = (op == ORC_LE) ? ORC_GE : ORC_LE;
+        logcol[i] = -1;
+        if (op != ORC_EQ) {
+            logcol[i] = (int32_t)k;
+            var_ids[k++] = (int32_t)(n + i);
+        }
+        if (op == ORC_GE) ++n_ge;
+    }
+    f.n_real = k;
+    for (int64_t i = 0; i < m; ++i) {
+        int op = ops[i];
+        if (b[i] < 0.0 && op != ORC_EQ) op = (op == ORC_LE) ? ORC_GE : ORC_LE;
+        artcol[i] = -1;
+        if (op != ORC_LE) {
+            artcol[i] = (int32_t)k;
+            var_ids[k++] = (int32_t)(art_base + i);
+        }
+    }
+    /* rows */
+    for (int64_t i = 0; i < m; ++i) {
+        double *row = f.T + i * W;
+        int op = ops[i];
+        const int neg = b[i] < 0.0;
+        if (neg && op != ORC_EQ) op = (op == ORC_LE) ? ORC_GE : ORC_LE;
+        for (int64_t j = 0; j < n; ++j) row[j] = neg ? -A[i * lda + j] : A[i * lda + j];
+        row[W - 1] = neg ? -b[i] : b[i];
+        if (op == ORC_LE) row[logcol[i]] = 1.0;
+        if (op == ORC_GE) row[logcol[i]] = -1.0;
+        if (op != ORC_LE) row[artcol[i]] = 1.0;
+        f.basis[i] = (op == ORC_LE) ? logcol[i] : artcol[i];
+        f.is_basic[f.basis[i]] = 1;
+    }
+    for (int64_t j = 0; j < n; ++j) f.T[m * W + j] = c[j];
+    const int two = R == m + 2;
+    if (two) {
+        /* w = sum of the artificials, expressed in the non-basic variables: minus the sum of the artificial rows */
+        double *w = f.T + (m + 1) * W;
+        for (int64_t j = 0; j < W; ++j) {
+            if (j < W - 1 && f.is_basic[j]) continue;
+            double acc = 0.0;
+            for (int64_t i = 0; i < m; ++i)
+                if (artcol[i] >= 0) acc = acc + f.T[i * W + j];
+            w[j] = -acc;
+        }
+    }
+    orcf_log L;
+    L.n_pivots = 0;
+    L.cap = cap;
+    L.snaps = snaps;
+    L.piv_row = piv_row;
+    L.piv_col = piv_col;
+    memcpy(snaps, f.T, (size_t)(R * W) * sizeof(double));
+
+    const int is_auto = o->max_pivots >= ORC_AUTO_BUDGET;
+    const int64_t cap_piv = is_auto ? orc_auto_cap(m, n + n_ge + 1) : o->max_pivots;
+    int64_t budget = cap_piv;
+    int32_t rule = o->rule;
+    int st = ORC_OPT;
+    int64_t n_phase1 = 0;
+    if (two) {
+        st = orcf_phase(&f, m + 1, rule, o, budget, &L);
+        if (st == ORC_LIMIT && is_auto && rule == ORC_RULE_DANTZIG) {
+            rule = ORC_RULE_BLAND;
+            budget += cap_piv;
+            st = orcf_phase(&f, m + 1, rule, o, budget, &L);
+        }
+        if (st == ORC_UNBOUNDED) st = ORC_NUMERICAL;
+        if (st == ORC_OPT && f.T[(m + 1) * W + W - 1] < -o->eps_feas) st = ORC_INFEASIBLE;
+        if (st == ORC_OPT) {
+            /* artificials still basic at level zero leave on the largest eligible entry of their row */
+            for (int64_t i = 0; i < m && st == ORC_OPT; ++i) {
+                if (f.basis[i] < f.n_real) continue; /* also skips nothing negative: flags are set below */
+                const double *row = f.T + i * W;
+                int64_t best = -1;
+                double best_abs = 0.0;
+                for (int64_t j = 0; j < f.n_real; ++j) {
+                    if (f.is_basic[j]) continue;
+                    double a = fabs(row[j]);
+                    if (!(a > o->eps_pivot)) continue;
+                    if (best < 0 || a > best_abs) {
+                        best = j;
+                        best_abs = a;
+                    }
+                }
+                if (best < 0) {
+                    f.basis[i] = -1 - f.basis[i];
+                    continue;
+                }
+                if (L.n_pivots >= budget) {
+                    st = ORC_LIMIT;
+                    break;
+                }
+                orcf_pivot(&f, i, best);
+                orcf_record(&f, &L, i, best);
+            }
+        }
+        n_phase1 = L.n_pivots;
+    }
+    if (st == ORC_OPT) {
+        st = orcf_phase(&f, m, rule, o, budget, &L);
+        if (st == ORC_LIMIT && is_auto && rule == ORC_RULE_DANTZIG) {
+            rule = ORC_RULE_BLAND;
+            budget += cap_piv;
+            st = orcf_phase(&f, m, rule, o, budget, &L);
+        }
+    }
+    for (int64_t i = 0; i < m; ++i) {
+        const int32_t bi = f.basis[i] < 0 ? -1 - f.basis[i] : f.basis[i];
+        basis_out[i] = f.basis[i] < 0 ? -1 - var_ids[bi] : var_ids[bi];
+    }
+    out[0] = R;
+    out[1] = W;
+    out[2] = L.n_pivots;
+    out[3] = st;
+    out[4] = n_phase1;
+    out[5] = art_base;
+    free(f.T);
+    free(f.basis);
+    free(f.is_basic);
+    free(logcol);
+    free(artcol);
     return 0;
 }
 

@@ -92,19 +92,23 @@ struct DevBuf {
     ~DevBuf() { release(); }  // b200lp_destroy deletes the solver: whatever it did not release by name goes here
 };
 
+// Everything a captured kernel launch bakes into the graph: the tableau binding, the options, and EVERY device pointer
+// handed to a kernel of the loop.  A workspace is reused across unrelated problems (thread_solver), so two problems
+// with the same R, C and tableau address but different m / art_base / label buffers must not share a graph.
 struct GraphKey {
     const double* T = nullptr;
-    int64_t R = 0, C = 0, ld = 0, obj_row = -1;
-    int32_t rule = -1, variant = -1, iters = 0;
+    int64_t R = 0, C = 0, ld = 0, obj_row = -1, m = -1;
+    int32_t rule = -1, variant = -1, iters = 0, art_base = -1;
     double eps_cost = 0, eps_pivot = 0;
     int64_t hist_cap = 0;
     const double* snaps = nullptr;
     int64_t snap_cap = 0;
     int32_t blocked_k = 0;  // 0: rank-1 iterations; K > 0: look-ahead blocks of K pivots
+    const void* ptrs[12] = {};  // rowlab, collab, col, history x 4, look-ahead buffers x 5
     bool operator==(const GraphKey& o) const {
         return blocked_k == o.blocked_k && snaps == o.snaps && snap_cap == o.snap_cap && T == o.T && R == o.R && C == o.C && ld == o.ld && obj_row == o.obj_row && rule == o.rule &&
                variant == o.variant && iters == o.iters && eps_cost == o.eps_cost && eps_pivot == o.eps_pivot &&
-               hist_cap == o.hist_cap;
+               hist_cap == o.hist_cap && m == o.m && art_base == o.art_base && memcmp(ptrs, o.ptrs, sizeof(ptrs)) == 0;
     }
 };
 
@@ -336,11 +340,7 @@ B200LP_API int b200lp_set_stream(b200lp_solver* s, void* stream) {
     // the handle is used as given: 0 is the legacy default stream (explicitly requested by the caller; CUDA
     // graphs cannot be captured on it, so the loop falls back to plain launches there)
     s->stream = (cudaStream_t)stream;
-    if (s->graph) {
-        cudaGraphExecDestroy(s->graph);
-        s->graph = nullptr;
-        s->graph_key = GraphKey();
-    }
+    drop_graph(s);
     return 0;
 }
 
@@ -808,6 +808,11 @@ static int get_graph(b200lp_solver* s, const b200lp_opts* o, int64_t obj_row, in
     k.hist_cap = s->hist_cap;
     k.snaps = s->snaps;
     k.snap_cap = s->snap_cap;
+    k.m = s->m;
+    k.art_base = s->art_base;
+    const void* baked[12] = {s->rowlab.p, s->collab.p, s->col.p, s->h_row.p, s->h_col.p, s->h_enter.p, s->h_leave.p,
+                             s->blk.pend, s->blk.colP, s->blk.qP, s->blk.objcur, s->blk.rhscur};
+    memcpy(k.ptrs, baked, sizeof(baked));
     if (s->graph && k == s->graph_key) return 0;
     if (s->graph) {
         cudaGraphExecDestroy(s->graph);
@@ -1231,6 +1236,7 @@ B200LP_API int b200lp_set_snapshots(b200lp_solver* s, double* snaps_dev, int64_t
     if (!s) return fail(B200LP_E_INVALID, "solver is NULL");
     s->snaps = (snaps_dev && cap > 0) ? snaps_dev : nullptr;
     s->snap_cap = s->snaps ? cap : 0;
+    drop_graph(s);  // the snapshot buffer is baked into the captured launches (and allocators hand addresses out again)
     return 0;
 }
 

@@ -75,11 +75,12 @@ class B200LPError(RuntimeError):
     pass
 
 
-def build(verbose: bool = False) -> str:
-    """Compile libb200lp.so in-tree for sm_100a (nvcc cross-compiles without a GPU)."""
+def build(verbose: bool = False, force: bool = False) -> str:
+    """Compile libb200lp.so in-tree for sm_100a (nvcc cross-compiles without a GPU).  Without `force` an existing
+    library newer than every source is kept (the GPU box has the prebuilt file and nothing to rebuild it for)."""
     src = os.path.join(CSRC, "b200lp.cu")
     deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC)] + [os.path.join(_HERE, "..", "include", "b200lp.h")]
-    if os.path.exists(LIB_PATH) and all(os.path.getmtime(LIB_PATH) >= os.path.getmtime(d) for d in deps):
+    if not force and os.path.exists(LIB_PATH) and all(os.path.getmtime(LIB_PATH) >= os.path.getmtime(d) for d in deps):
         return LIB_PATH
     cmd = ["nvcc"] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB_PATH, src]
     subprocess.check_call(cmd, cwd=CSRC)
@@ -183,6 +184,27 @@ def _ptr(a):
     return a.ctypes.data_as(C.c_void_p)
 
 
+def _check_lp_arrays(A, b, c, ops):
+    """Host arrays of one LP -> contiguous (A, b, c, ops, m, n); raises ValueError on any shape disagreement (the C ABI
+    takes plain pointers and sizes and would read past the end of a short buffer)."""
+    b = np.ascontiguousarray(b, dtype=np.float64)
+    c = np.ascontiguousarray(c, dtype=np.float64)
+    ops = np.ascontiguousarray(ops, dtype=np.int8)
+    if b.ndim != 1 or c.ndim != 1:
+        raise ValueError(f"b and c must be vectors, got shapes {b.shape} and {c.shape}")
+    m, n = len(b), len(c)
+    A = np.ascontiguousarray(A, dtype=np.float64)
+    if A.size == 0 and m * n == 0:
+        A = A.reshape(m, n)
+    if A.shape != (m, n):
+        raise ValueError(f"A has shape {A.shape}, expected (len(b), len(c)) = {(m, n)}")
+    if ops.shape != (m,):
+        raise ValueError(f"ops has shape {ops.shape}, expected ({m},)")
+    if m and (ops.min() < 0 or ops.max() > 2):
+        raise ValueError("ops entries must be 0 ('<='), 1 ('>=') or 2 ('=')")
+    return A, b, c, ops, m, n
+
+
 class Solver:
     """Owning wrapper of one b200lp_solver workspace (one per thread; see `thread_solver`)."""
 
@@ -246,11 +268,10 @@ class Solver:
         opts = opts or make_opts()
         ops = np.ascontiguousarray(ops, dtype=np.int8)
         if not on_device:
-            A = np.ascontiguousarray(A, dtype=np.float64)
-            b = np.ascontiguousarray(b, dtype=np.float64)
-            c = np.ascontiguousarray(c, dtype=np.float64)
-            m, n = len(b), len(c)
+            A, b, c, ops, m, n = _check_lp_arrays(A, b, c, ops)
             lda = n
+        elif m is None or n is None or ops.shape != (m,):
+            raise ValueError(f"on_device: m and n must be given and ops must have m = {m} entries, got {ops.shape}")
         p = Problem(m, n, lda if lda else n, _ptr(A), _ptr(b), _ptr(c), _ptr(ops), 1 if on_device else 0, 0)
         res, keep = self._result(n, hist_cap)
         check(lib().b200lp_solve_dense(self._h, C.byref(p), C.byref(opts), C.byref(res)))
@@ -258,11 +279,7 @@ class Solver:
 
     def build_dense(self, A, b, c, ops):
         """First half of solve_dense: build the initial tableau on the device (host ndarrays in)."""
-        A = np.ascontiguousarray(A, dtype=np.float64)
-        b = np.ascontiguousarray(b, dtype=np.float64)
-        c = np.ascontiguousarray(c, dtype=np.float64)
-        ops = np.ascontiguousarray(ops, dtype=np.int8)
-        m, n = len(b), len(c)
+        A, b, c, ops, m, n = _check_lp_arrays(A, b, c, ops)
         p = Problem(m, n, n, _ptr(A), _ptr(b), _ptr(c), _ptr(ops), 0, 0)
         check(lib().b200lp_build_dense(self._h, C.byref(p)))
         mm, n_obj, Ccols, ld = self.dims()
@@ -412,7 +429,12 @@ class Solver:
         b = np.ascontiguousarray(b, dtype=np.float64)
         c = np.ascontiguousarray(c, dtype=np.float64)
         ops = np.ascontiguousarray(ops, dtype=np.int8)
+        if A.ndim != 3:
+            raise ValueError(f"A must be [B, m, n], got shape {A.shape}")
         B, m, n = A.shape
+        if b.shape != (B, m) or c.shape != (B, n) or ops.shape != (B, m):
+            raise ValueError(f"batched LP shapes disagree: A {A.shape}, b {b.shape} (want {(B, m)}), "
+                             f"c {c.shape} (want {(B, n)}), ops {ops.shape} (want {(B, m)})")
         status = np.empty(B, dtype=np.int32)
         fun = np.empty(B, dtype=np.float64)
         npiv = np.empty(B, dtype=np.int32)

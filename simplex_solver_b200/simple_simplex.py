@@ -139,6 +139,14 @@ def optimize_json_format(tableau, maximize: bool | None = None, rule: str = "dan
         steps.append({"step": it + 1, "pivotRowIndex": r, "pivotColIndex": where[enter],
                       "tableau": expand_full(host[it], rl, cl, var_ids, m).tolist(),
                       "basis": [int(v) for v in rl[:m]]})
+    if k == res["n_pivots"]:
+        # the labels replayed on the host from the pivot history must be the device's own (a row flagged redundant
+        # by the drive-out holds -1 - id there): a mismatch means the displayed basic columns would be wrong
+        rl_dev, cl_dev = solver.get_labels()
+        flagged = rl_dev[:m] < 0
+        if not (np.array_equal(np.where(flagged, -1 - rl_dev[:m], rl_dev[:m]), rl[:m])
+                and np.array_equal(cl_dev[:C - 1], cl[:C - 1])):
+            raise RuntimeError("pivotSteps: label replay disagrees with the device labels")
     z = None
     if res["status"] == native.STATUS_OPTIMAL:
         z = -res["fun"] if maximize else res["fun"]

@@ -55,7 +55,9 @@ def _json_default(o):
 
 
 class SolverController:
-    """Drop-in for the reference class of the same name; `output_dir=None` skips writing solucion_N.json."""
+    """Drop-in for the reference class of the same name.  `output_dir`: where `solucion_N.json` is written; the
+    reference always saves into its configured OUTPUT_DIR (storage_service.py:106-112) -- pass that directory for the
+    same behaviour; the default None (library use, tests, benchmarks) writes no file."""
 
     def __init__(self, problem_data_wrapper: dict, output_dir: Optional[str] = None, rule: str = "dantzig",
                  device: int = 0, verbose: bool = False):
@@ -203,11 +205,13 @@ class SolverController:
 
 
 def save_solution(report: dict, output_dir: str, prefix: str = "solucion_") -> str:
-    """Sequential `solucion_N.json`, as StorageService.save_solution (storage_service.py:35-43, :75-88, :106-112)."""
+    """`solucion_N.json` with N the FIRST free number counting from 1 -- gaps left by deleted files are filled, as
+    StorageService._get_next_filename does (storage_service.py:35-43; save_solution :106-112)."""
     os.makedirs(output_dir, exist_ok=True)
-    nums = [int(f[len(prefix):-5]) for f in os.listdir(output_dir)
-            if f.startswith(prefix) and f.endswith(".json") and f[len(prefix):-5].isdigit()]
-    path = os.path.join(output_dir, f"{prefix}{max(nums, default=0) + 1}.json")
+    k = 1
+    while os.path.exists(os.path.join(output_dir, f"{prefix}{k}.json")):
+        k += 1
+    path = os.path.join(output_dir, f"{prefix}{k}.json")
     with open(path, "w", encoding="utf-8") as f:
         json.dump(report, f, indent=4, ensure_ascii=False, default=_json_default)
     return path

@@ -179,3 +179,31 @@ def test_linprog_rejects_unsupported_bounds():
         _check_bounds([(1, None)], 1)
     with pytest.raises(NotImplementedError):
         _check_bounds([(0, 5.0)], 1)
+
+
+def test_save_solution_fills_gaps_like_the_reference(tmp_path):
+    """storage_service.py:35-43 probes 1, 2, ... for the first free name: a deleted solucion_1.json is reused."""
+    rep = {"solucion_encontrada": {}}
+    paths = [save_solution(rep, str(tmp_path)) for _ in range(3)]
+    import os
+    os.remove(paths[0])
+    assert save_solution(rep, str(tmp_path)).endswith("solucion_1.json")
+    assert save_solution(rep, str(tmp_path)).endswith("solucion_4.json")
+
+
+def test_array_shapes_are_validated_before_the_c_abi():
+    """The C ABI takes plain pointers and sizes: a short buffer must be a Python error, never an out-of-bounds read."""
+    chk = native._check_lp_arrays
+    A, b, c, ops = np.ones((3, 2)), np.ones(3), np.ones(2), np.zeros(3, dtype=np.int8)
+    assert chk(A, b, c, ops)[4:] == (3, 2)
+    assert chk(np.zeros((0, 2)), np.zeros(0), c, np.zeros(0, dtype=np.int8))[4:] == (0, 2)
+    assert chk([], np.zeros(0), c, [])[0].shape == (0, 2)
+    for bad in ((np.ones((2, 2)), b, c, ops), (np.ones((3, 3)), b, c, ops), (A, b, c, ops[:2]), (A, b, np.ones((2, 1)), ops),
+                (A, b, c, np.array([0, 1, 3], dtype=np.int8)), (np.ones(6), b, c, ops)):
+        with pytest.raises(ValueError):
+            chk(*bad)
+    s = object.__new__(native.Solver)  # no device needed: the checks run before the library is touched
+    with pytest.raises(ValueError):
+        native.Solver.solve_batched(s, np.ones((4, 3, 2)), np.ones((4, 2)), np.ones((4, 2)), np.zeros((4, 3)), opts=object())
+    with pytest.raises(ValueError):
+        native.Solver.solve_batched(s, np.ones((3, 2)), np.ones(3), np.ones(2), np.zeros(3), opts=object())
