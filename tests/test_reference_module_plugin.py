@@ -24,9 +24,15 @@ needs_reference = pytest.mark.skipif(not os.path.isdir(os.path.join(REFERENCE, "
 
 
 def _reference_module():
-    sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
-    import make_golden
-    return make_golden.import_reference_controller()
+    """Import the reference controller once; sys.path is restored afterwards (the reference has a `tests` package of
+    its own that must not shadow this repo's in processes spawned later)."""
+    saved = list(sys.path)
+    try:
+        sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
+        import make_golden
+        return make_golden.import_reference_controller()
+    finally:
+        sys.path[:] = saved
 
 
 def _problems():
