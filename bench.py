@@ -117,7 +117,8 @@ def cpu_pivots_per_s(R, C_total, rule, pivots, seed, threads=None, repeats=1):
     """Oracle (OpenMP) on a generated R x C_total tableau: (pivots/s, threads, seconds)."""
     from oracle import oracle as O
     O.build()
-    threads = threads or O.max_threads()
+    threads = threads or O.host_cores()
+    O.set_threads(threads)
     t = O.OracleTableau.generate(seed, R - 1, C_total - 1)
     best = None
     for _ in range(repeats):
@@ -130,24 +131,27 @@ def cpu_pivots_per_s(R, C_total, rule, pivots, seed, threads=None, repeats=1):
 
 
 def run_reference_arm(args):
-    """--impl reference: the CPU implementation of the path on this box's host cores, same config/metric/unit."""
+    """--impl reference: the CPU implementation of the path on this box's host cores, same config/metric/unit.
+
+    Threads = every core this process may run on (its affinity mask), passed to OpenMP explicitly: torchrun exports
+    OMP_NUM_THREADS=1 to its workers, which is a launcher default, not a property of the CPU path.  A 1-core figure of
+    the same sample is printed beside the all-core one ("1 core and all host cores")."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     R = args.rows
-    C = args.rows if args.gpus == 1 else args.rows  # the CPU arm always times a square slab of the config's row count
-    sample_rows = R
-    note = f"{args.ref_pivots} pivots per step on the full {R} x {C} tableau"
+    C = args.cols_total
+    extrapolated = False
     if args.gpus > 1:
-        # config 5 does not fit host-side timing budgets: time a 16384-column slab and scale by columns (extrapolated)
+        # config 5 (137 GB) does not fit host-side timing budgets: time a 16384-column slab of it and scale by columns
         C = 16384
-        note = (f"{args.ref_pivots} pivots per step on a {R} x {C} column slab of the {R} x {args.cols_total} tableau, "
-                f"scaled by {C}/{args.cols_total} (extrapolated)")
+        extrapolated = True
     from oracle import oracle as O
     O.build()
-    threads = O.max_threads()
+    threads = O.host_cores()
+    O.set_threads(threads)
     rule = 1 if args.rule == "bland" else 0
-    tab = O.OracleTableau.generate(args.seed, sample_rows - 1, C - 1)
+    tab = O.OracleTableau.generate(args.seed, R - 1, args.cols_total - 1, 0, C - 1)
     opts = O.make_opts(rule=rule, max_pivots=args.ref_pivots, threads=threads)
     for _ in range(args.warmup):
         tab.solve(opts)
@@ -156,18 +160,30 @@ def run_reference_arm(args):
     for _ in range(args.steps):
         n += tab.solve(opts)["n_pivots"]
     dt = time.perf_counter() - t0
-    pps = n / dt
-    if args.gpus > 1:
-        pps *= C / args.cols_total
+    scale = C / args.cols_total
+    pps = n / dt * scale
+    # the same sample on ONE core (a quarter of the pivots of one step: it is ~`threads` times slower)
+    one_piv = max(2, args.ref_pivots // 4)
+    t1 = time.perf_counter()
+    n1 = tab.solve(O.make_opts(rule=rule, max_pivots=one_piv, threads=1))["n_pivots"]
+    pps1 = n1 / (time.perf_counter() - t1) * scale
     bpp = 16.0 * args.rows * args.cols_total
     gbps = pps * bpp / 1e9
+    note = (f"{args.ref_pivots} pivots per step on " +
+            (f"a {R} x {C} column slab of the {R} x {args.cols_total} tableau, scaled by {C}/{args.cols_total} (extrapolated)"
+             if extrapolated else f"the full {R} x {C} tableau") +
+            f"; oracle/ (C restatement, OpenMP) on {threads} threads")
     line = {
         "impl": "reference", "metric": METRIC, "value": gbps, "unit": "GB/s", "pivots_per_s": pps, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True,
         "scaling": "strong" if args.gpus > 1 else "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": workload_config(args),
+        "reference_sample": {"pivots_per_step": args.ref_pivots, "rows": R, "cols": C, "extrapolated": extrapolated,
+                             "scale_to_full_tableau": scale, "omp_num_threads_env": os.environ.get("OMP_NUM_THREADS")},
         "cpu_baseline": {"value": gbps, "unit": "GB/s", "pivots_per_s": pps, "cores": threads, "kind": "port",
-                         "sample": note, "host_cpus": os.cpu_count()},
+                         "sample": note, "host_cpus": os.cpu_count(),
+                         "one_core": {"value": pps1 * bpp / 1e9, "unit": "GB/s", "pivots_per_s": pps1, "cores": 1,
+                                      "sample": f"{one_piv} pivots of the same sample"}},
         "e2e": {"value": gbps, "unit": "GB/s", "pivots_per_s": pps, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -179,6 +195,7 @@ def workload_config(args):
         return {"workload": f"BASELINE config 4: single dense {args.rows}x{args.rows} fp64 condensed tableau, "
                             f"{args.rule} rule, fixed budget of {args.pivots} pivots per step",
                 "rows": args.rows, "cols": args.rows, "rule": args.rule, "pivots_per_step": args.pivots,
+                "generator": getattr(args, "generator", "counter"),
                 "bytes_per_pivot": 16 * args.rows * args.rows,
                 "l2": f"tableau ({8 * args.rows * args.rows / 1e9:.2f} GB) vs L2 (0.126 GB): every pivot streams it from HBM",
                 "parallelism": "1 GPU"}
@@ -188,6 +205,74 @@ def workload_config(args):
             "bytes_per_pivot": 16 * args.rows * args.cols_total,
             "l2": "each shard is far larger than L2", "parallelism": f"column-sharded x{args.gpus}, "
             "1 exchange of candidate columns per pivot (see 'collective')"}
+
+
+# ----------------------------------------------------------------------------------------------------------
+# parity of the timed run: pivot history against the committed oracle sequence
+# ----------------------------------------------------------------------------------------------------------
+def expected_history(args):
+    """(row, entering id, leaving id) of the first pivots of this config under Bland, computed by the CPU oracle
+    (tests/golden/make_pivot_history.py).  None when the run is not one of the two committed configs."""
+    if args.rule != "bland" or args.seed != 4 or getattr(args, "generator", "counter") != "counter":
+        return None
+    name = {(16384, 16384): "config4", (131072, 131072): "config5"}.get((args.rows, args.cols_total))
+    if not name:
+        return None
+    try:
+        return np.load(os.path.join(ROOT, "tests", "golden", f"pivot_history_{name}.npy"))
+    except Exception:
+        return None
+
+
+class HistoryCheck:
+    """Collects the pivot history of consecutive steps that start from a freshly generated tableau and compares it with
+    the oracle's sequence; the SHA-256 is over the int32 triples (row, entering id, leaving id) in pivot order."""
+
+    def __init__(self, args):
+        self.want = expected_history(args)
+        self.rows = []
+
+    def add(self, h):
+        self.rows.append(np.stack([h["piv_row"], h["enter_lab"], h["leave_lab"]], axis=1).astype(np.int32))
+
+    def report(self):
+        import hashlib
+        got = np.concatenate(self.rows, axis=0) if self.rows else np.zeros((0, 3), np.int32)
+        out = {"pivots": int(len(got)), "sha256": hashlib.sha256(np.ascontiguousarray(got).tobytes()).hexdigest()}
+        if self.want is not None:
+            k = min(len(got), len(self.want))
+            out["compared_with_oracle"] = int(k)
+            out["equals_oracle"] = bool(np.array_equal(got[:k], self.want[:k]))
+            out["oracle_sha256"] = hashlib.sha256(np.ascontiguousarray(self.want[:len(got)]).tobytes()).hexdigest() \
+                if len(self.want) >= len(got) else None
+        return out
+
+
+def single_gpu_parity_cases(device=0):
+    """Small invocations of every loop of the single-GPU path, bit for bit against the oracle (pivots and tableau)."""
+    from oracle import oracle as O
+    from simplex_solver_b200 import native
+    import torch
+    s = native.Solver(device)
+    cases, ok = 0, True
+    for (m, n, budget) in ((511, 767, 96), (130, 257, 60)):
+        ld = (n + 1 + 15) // 16 * 16
+        for rule in (native.RULE_BLAND, native.RULE_DANTZIG):
+            ot = O.OracleTableau.generate(4, m, n)
+            ref = ot.solve(O.make_opts(rule=rule, max_pivots=budget), hist_cap=budget)
+            for kw in (dict(loop_mode=native.LOOP_GRAPH, update_variant=native.UPDATE_LDG),
+                       dict(loop_mode=native.LOOP_GRAPH, update_variant=native.UPDATE_TMA),
+                       dict(loop_mode=native.LOOP_AUTO), dict(loop_mode=native.LOOP_BLOCKED, check_every=24)):
+                T = torch.empty((m + 1) * ld, dtype=torch.float64, device=f"cuda:{device}")
+                s.attach(T.data_ptr(), m, 1, n + 1, ld, n, n + m, keep=T)
+                s.generate(4, n, 0)
+                got = s.run(native.make_opts(rule=rule, max_pivots=budget, **kw), hist_cap=budget)
+                good = (got["n_pivots"] == ref["n_pivots"] and np.array_equal(got["piv_row"], ref["piv_row"])
+                        and np.array_equal(got["enter_lab"], ref["enter_lab"]) and np.array_equal(s.read_tableau(), ot.T))
+                cases += 1
+                ok = ok and bool(good)
+    s.close()
+    return cases, ok
 
 
 # ----------------------------------------------------------------------------------------------------------
@@ -214,12 +299,40 @@ def _bench_single_gpu(args):
     s.set_stream(torch.cuda.current_stream().cuda_stream)
     T = torch.empty(R * ld, dtype=torch.float64, device="cuda:0")
     s.attach(T.data_ptr(), m, 1, C, ld, n, n + m, keep=T)
-    s.generate(args.seed, n, 0)
+    if args.generator == "survey":
+        # SURVEY.md 8d's literal definition of config 4: the config-2 generator (numpy default_rng) with seed 4,
+        # A ~ U[0,1), b = A x0 + U[0.1,1), c ~ U[0.1,1), maximise -- built on the host once and uploaded per refresh
+        from simplex_solver_b200 import workloads as W
+        A_s, b_s, c_s, ops_s, _ = W.dense_feasible_lp(n, seed=args.seed, m=m)
+        T.view(R, ld)[:m, :n].copy_(torch.from_numpy(A_s))
+        T.view(R, ld)[:m, n].copy_(torch.from_numpy(b_s))
+        T.view(R, ld)[m, :n].copy_(torch.from_numpy(-c_s))
+        T.view(R, ld)[m, n] = 0.0
+        torch.cuda.synchronize()
+        T0 = T.clone()
+        rl0 = np.concatenate([n + np.arange(m), [-1]]).astype(np.int32)
+        cl0 = np.concatenate([np.arange(n), [-1]]).astype(np.int32)
+        del A_s
+
+        def fresh():
+            s.attach(T.data_ptr(), m, 1, C, ld, n, n + m, keep=T)   # also clears the loop state
+            T.copy_(T0)
+            s.set_labels(rl0, cl0)
+    else:
+        def fresh():
+            s.generate(args.seed, n, 0)
+    fresh()
     torch.cuda.synchronize()
     # the headline is the rank-1 loop that north_star specifies (one fused tableau pass per pivot): LOOP_GRAPH is set
     # explicitly because the library's AUTO mode would pick the look-ahead loop for a tableau of this size
     opts = native.make_opts(rule=rule, max_pivots=args.pivots, update_variant=variant, loop_mode=native.LOOP_GRAPH)
     bytes_per_pivot = 16.0 * R * C
+
+    # parity before anything is timed: every loop of the path on small tableaux, bit for bit against the oracle
+    parity = None
+    if args.parity:
+        n_cases, ok = single_gpu_parity_cases(0)
+        parity = {"cases": n_cases, "ok": ok, "checker": "oracle/ (pivot history and tableau bits)"}
 
     launches = 0
     sampler = ClockSampler(0)
@@ -227,20 +340,28 @@ def _bench_single_gpu(args):
     sampler.wait_first()
     for _ in range(args.warmup):
         s.run(opts)
+    # the timed steps start from the freshly generated tableau, so that their pivot history is a prefix of the sequence
+    # the oracle computed for this config (tests/golden/pivot_history_config4.npy)
+    fresh()
     torch.cuda.synchronize()
+    hist = HistoryCheck(args)
     sampler.mark()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record()
     pivots = 0
     for _ in range(args.steps):
-        r = s.run(opts)
+        r = s.run(opts, hist_cap=args.pivots)
         pivots += r["n_pivots"]
         launches += r["kernel_launches"]
+        hist.add(r)
     ev1.record()
     torch.cuda.synchronize()
     clocks = sampler.stop()
     sec = ev0.elapsed_time(ev1) * 1e-3
     value = pivots / sec
+    if parity is not None:
+        parity["timed_history"] = hist.report()
+        parity["ok"] = parity["ok"] and parity["timed_history"].get("equals_oracle", True)
 
     # live per-kernel durations of a real loop (events around every launch)
     prof = s.profile_loop(opts, iters=min(64, args.pivots))
@@ -266,24 +387,31 @@ def _bench_single_gpu(args):
     if args.lookahead:
         lookahead = {}
         for K in (8, 16, 32):
-            s.generate(args.seed, n, 0)
+            fresh()
             ob = native.make_opts(rule=rule, max_pivots=args.pivots * 4, loop_mode=native.LOOP_BLOCKED, check_every=K)
             s.run(ob)
             torch.cuda.synchronize()
             b0, b1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            fresh()
+            torch.cuda.synchronize()
             b0.record()
-            rb = s.run(ob)
+            rb = s.run(ob, hist_cap=args.pivots * 4)
             b1.record()
             torch.cuda.synchronize()
             pps = rb["n_pivots"] / (b0.elapsed_time(b1) * 1e-3)
+            hk = HistoryCheck(args)
+            hk.add(rb)
             lookahead[f"K={K}"] = {"pivots_per_s": pps, "speedup_vs_rank1_loop": pps / value,
-                                   "hbm_bytes_per_pivot": bytes_per_pivot / K, "kernel_launches": rb["kernel_launches"]}
+                                   "hbm_bytes_per_pivot": bytes_per_pivot / K, "kernel_launches": rb["kernel_launches"],
+                                   "history": hk.report()}
+            if parity is not None:
+                parity["ok"] = parity["ok"] and lookahead[f"K={K}"]["history"].get("equals_oracle", True)
         lookahead["note"] = ("loop_mode=BLOCKED: K pivots are decided from O(R+C) state and applied in one pass over the "
                              "tableau; pivot sequence and tableau are bit-identical to the rank-1 loop (tests), HBM traffic "
                              "per pivot is 2*R*C*8/K, so pivots/s is no longer bounded by the rank-1 roofline")
 
     # ---- e2e: the reference-facing call with HOST buffers (pinned), copies inside the timed region ----
-    s.generate(args.seed, n, 0)
+    fresh()
     torch.cuda.synchronize()
     Th = torch.empty((R, ld), dtype=torch.float64, pin_memory=True)
     Th.copy_(T.view(R, ld))
@@ -352,11 +480,77 @@ def _bench_single_gpu(args):
         "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
         "gpu_launches": int(launches), "clocks": clocks,
     }
+    if parity is not None:
+        line["parity"] = parity
     if lookahead:
         line["lookahead"] = lookahead
     if args.secondary:
         line["secondary"] = secondary_configs(args)
+    if args.config5_one_gpu:
+        line["config5_one_gpu"] = config5_on_one_gpu(args)
     print(json.dumps(line))
+    if parity is not None and not parity["ok"]:
+        print("[bench] PARITY FAILURE: the GPU path differs from the oracle", file=sys.stderr)
+        sys.exit(3)
+
+
+def config5_on_one_gpu(args):
+    """BASELINE config 5's tableau (131072 x 131072 fp64, 137.4 GB) on ONE B200: the same LP the 2/4/8-GPU lines
+    shard, as a same-workload anchor of the 1 -> 8 curve (non-headline).  Skipped when the device has no room."""
+    import torch
+    from simplex_solver_b200 import native
+    R = C = 131072
+    need = 8 * R * C + (6 << 30)
+    torch.cuda.empty_cache()
+    free, total = torch.cuda.mem_get_info()
+    if free < need:
+        return {"skipped": f"needs {need / 1e9:.1f} GB of HBM, {free / 1e9:.1f} GB free"}
+    try:
+        T = torch.empty(R * C, dtype=torch.float64, device="cuda:0")
+        s = native.Solver(0)
+        s.set_stream(torch.cuda.current_stream().cuda_stream)
+        m = n = R - 1
+        s.attach(T.data_ptr(), m, 1, C, C, n, n + m, keep=T)
+        s.generate(args.seed, n, 0)
+        rule = native.RULE_BLAND if args.rule == "bland" else native.RULE_DANTZIG
+        piv = 8
+        o = native.make_opts(rule=rule, max_pivots=piv, loop_mode=native.LOOP_GRAPH, check_every=piv)
+        s.run(o)                                    # warm-up (graph capture)
+        s.generate(args.seed, n, 0)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        r = s.run(o, hist_cap=piv)
+        e1.record()
+        torch.cuda.synchronize()
+        sec = e0.elapsed_time(e1) * 1e-3
+        a5 = argparse.Namespace(rule=args.rule, seed=args.seed, rows=R, cols_total=C)
+        hk = HistoryCheck(a5)
+        hk.add(r)
+        out = {"rows": R, "cols": C, "pivots": r["n_pivots"], "pivots_per_s": r["n_pivots"] / sec,
+               "GBps": r["n_pivots"] / sec * 16.0 * R * C / 1e9, "loop": "rank-1 graph loop (k_update_tma)",
+               "history": hk.report()}
+        peak, _ = measured_peak()
+        out["frac_of_measured_peak"] = out["GBps"] / peak
+        s.generate(args.seed, n, 0)
+        ob = native.make_opts(rule=rule, max_pivots=64, loop_mode=native.LOOP_BLOCKED, check_every=32)
+        s.run(ob)
+        s.generate(args.seed, n, 0)
+        torch.cuda.synchronize()
+        e0.record()
+        rb = s.run(ob, hist_cap=64)
+        e1.record()
+        torch.cuda.synchronize()
+        hb = HistoryCheck(a5)
+        hb.add(rb)
+        out["lookahead_K32"] = {"pivots_per_s": rb["n_pivots"] / (e0.elapsed_time(e1) * 1e-3), "history": hb.report()}
+        s.close()
+        del T
+        torch.cuda.empty_cache()
+        return out
+    except Exception as exc:  # noqa: BLE001 -- an anchor, not the headline: report instead of failing the line
+        torch.cuda.empty_cache()
+        return {"skipped": f"{type(exc).__name__}: {exc}"}
 
 
 def _solve_dense_host_ptr(solver, A_h, b_h, c_h, ops_h, opts, m, n, lda):
@@ -494,13 +688,28 @@ def _bench_sharded(args, rank, local, world):
     from simplex_solver_b200.sharded import CudaShardEngine, ShardedTableau
     R = args.rows
     m = R - 1
-    c_loc = args.cols_total // world            # stored columns per shard, RHS replica included
-    ncols = c_loc - 1
-    n_total = world * ncols
+    # ONE LP whatever the number of GPUs: n_total = cols_total - 1 structural variables, the same pivot sequence at
+    # 1, 2, 4 and 8 GPUs.  Every shard stores its slice plus an RHS replica: cols_total / world columns, the last one
+    # world - 1 more.
+    n_total = args.cols_total - 1
+    lo, hi = ShardedTableau.columns_of_tableau(args.cols_total, world, rank)
+    ncols = hi - lo
+    c_loc = ncols + 1                           # stored columns of this shard, RHS replica included
     rule = native.RULE_BLAND if args.rule == "bland" else native.RULE_DANTZIG
     opts = native.make_opts(rule=rule, max_pivots=args.pivots)
 
-    eng = CudaShardEngine(m, n_total, rank * ncols, ncols, args.seed, device=local)
+    # parity before anything is timed: the sharded loops on small tableaux against the oracle, on these GPUs
+    parity = None
+    if args.parity:
+        sys.path.insert(0, ROOT)
+        from tests.sharded_parity import run_cases
+        n_cases, ok = run_cases(rank, world, local)
+        flag = torch.tensor([1 if ok else 0], dtype=torch.int32, device=f"cuda:{local}")
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        parity = {"cases": n_cases, "ok": bool(int(flag.item())), "ranks": world,
+                  "checker": "oracle/ (pivot history, labels and every shard's tableau bits; tests/sharded_parity.py)"}
+
+    eng = CudaShardEngine(m, n_total, lo, ncols, args.seed, device=local)
     exchange = args.exchange
     if exchange == "p2p":  # candidates stored straight into every peer's region over NVLink (no collective)
         # symmetric memory needs peer access between all GPUs of the node; if any rank cannot set it up, every rank
@@ -524,8 +733,12 @@ def _bench_sharded(args, rank, local, world):
         sampler.wait_first()
     for _ in range(args.warmup):
         drv.run(opts, args.pivots, check_every=args.pivots)
+    # the timed steps start from the freshly generated tableau: their pivot history is a prefix of the sequence the
+    # oracle computed for this config (tests/golden/pivot_history_config5.npy), identical at every number of GPUs
+    eng.regenerate()
     torch.cuda.synchronize()
     dist.barrier()
+    hist = HistoryCheck(args)
     sampler.mark()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record()
@@ -533,6 +746,7 @@ def _bench_sharded(args, rank, local, world):
     for _ in range(args.steps):
         _, done_now = drv.run(opts, args.pivots, check_every=args.pivots)
         pivots += done_now
+        hist.add(eng.history(args.pivots))   # 3 x 4 x pivots bytes to the host, after the step's own status read
     ev1.record()
     torch.cuda.synchronize()
     dist.barrier()
@@ -542,6 +756,16 @@ def _bench_sharded(args, rank, local, world):
     sec = float(t.item())
     value = pivots / sec
     bytes_per_pivot = 16.0 * R * args.cols_total
+    if parity is not None:
+        rep = hist.report()
+        # every rank logged the same sequence?  (sum of per-rank "equals rank 0's hash" flags)
+        mine = torch.tensor([int(rep["sha256"][:15], 16)], dtype=torch.int64, device=f"cuda:{local}")
+        lo_h, hi_h = mine.clone(), mine.clone()
+        dist.all_reduce(lo_h, op=dist.ReduceOp.MIN)
+        dist.all_reduce(hi_h, op=dist.ReduceOp.MAX)
+        rep["identical_on_all_ranks"] = bool(int(lo_h.item()) == int(hi_h.item()))
+        parity["timed_history"] = rep
+        parity["ok"] = parity["ok"] and rep["identical_on_all_ranks"] and rep.get("equals_oracle", True)
 
     # roofline of the update kernel on this shard, timed alone on the launching stream
     upd_ms = eng.solver.time_update(1, 1, native.UPDATE_AUTO, 5)
@@ -567,6 +791,7 @@ def _bench_sharded(args, rank, local, world):
         for K in (16, 32):
             n_la = 2 * K
             drv.run(opts_la(native, rule, n_la), n_la, check_every=K, lookahead=K)   # warm-up + graph capture
+            eng.regenerate()
             torch.cuda.synchronize()
             dist.barrier()
             a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -577,26 +802,77 @@ def _bench_sharded(args, rank, local, world):
             tl = torch.tensor([a0.elapsed_time(a1) * 1e-3], dtype=torch.float64, device=f"cuda:{local}")
             dist.all_reduce(tl, op=dist.ReduceOp.MAX)
             pps = got / float(tl.item())
+            hk = HistoryCheck(args)
+            hk.add(eng.history(n_la))
             lookahead[f"K={K}"] = {"pivots_per_s": pps, "speedup_vs_rank1_loop": pps / value,
-                                   "hbm_bytes_per_pivot": bytes_per_pivot / K}
+                                   "hbm_bytes_per_pivot": bytes_per_pivot / K, "history": hk.report()}
+            if parity is not None:
+                parity["ok"] = parity["ok"] and lookahead[f"K={K}"]["history"].get("equals_oracle", True)
 
-    # e2e: inputs of this config cannot be staged through the host (137 GB); the end-to-end pass regenerates the
-    # shard on the device inside the timed region, runs the step and reads x*, z back to the host.
+    # e2e: every rank uploads its shard of the tableau from PINNED HOST memory inside the timed region (torch copy on
+    # the solver's stream into the attached device tableau), runs the step and reads x*, z back.  The host copy of the
+    # shard is made once, untimed (the generator is a device kernel; 137 GB cannot come from Python lists).  The step
+    # is `e2e_pivots` pivots, more than the 16 of a device-resident step, so that the 17-69 GB upload per rank does not
+    # stand alone in the figure (a real solve of this LP takes > 10^5 pivots).  Falls back to regenerating the shard on
+    # the device -- and says so -- when the host has no room to pin the tableau.
+    e2e_pivots = max(args.pivots, args.e2e_pivots)
+    shard_bytes_stored = 8 * eng.R * eng.ld
+    host_ok = False
+    if args.e2e_host != "off":
+        try:
+            import psutil
+            avail = psutil.virtual_memory().available
+        except Exception:  # noqa: BLE001
+            avail = 0
+        host_ok = args.e2e_host == "on" or avail > 2.5 * 8 * R * args.cols_total
+    hflag = torch.tensor([1 if host_ok else 0], dtype=torch.int32, device=f"cuda:{local}")
+    dist.all_reduce(hflag, op=dist.ReduceOp.MIN)
+    host_ok = bool(int(hflag.item()))
+    host_T = None
+    if host_ok:
+        try:
+            eng.regenerate()
+            host_T = torch.empty(eng.R * eng.ld, dtype=torch.float64, pin_memory=True)
+            host_T.copy_(eng.T)
+            torch.cuda.synchronize()
+        except Exception as exc:  # noqa: BLE001
+            print(f"[bench] rank {rank}: pinned host copy of the shard failed ({exc}); e2e regenerates on the device", file=sys.stderr)
+            host_T = None
+        hflag = torch.tensor([1 if host_T is not None else 0], dtype=torch.int32, device=f"cuda:{local}")
+        dist.all_reduce(hflag, op=dist.ReduceOp.MIN)
+        if int(hflag.item()) == 0:
+            host_T = None
+    o_e2e = native.make_opts(rule=rule, max_pivots=e2e_pivots)
+    rl0, cl0 = eng.initial_labels()
     dist.barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    eng.regenerate()
-    _, nq = drv.run(opts, args.pivots, check_every=args.pivots)
+    if host_T is not None:
+        eng.T.copy_(host_T, non_blocking=True)      # H2D of the whole shard on the solver's stream
+        eng.solver.set_labels(rl0, cl0)             # + its labels (host arrays)
+    else:
+        eng.regenerate()
+    _, nq = drv.run(o_e2e, e2e_pivots, check_every=args.pivots)
     x, fun = eng.solution()
     e1.record()
     torch.cuda.synchronize()
     t2 = torch.tensor([e0.elapsed_time(e1) * 1e-3], dtype=torch.float64, device=f"cuda:{local}")
     dist.all_reduce(t2, op=dist.ReduceOp.MAX)
     e2e = {"value": nq / float(t2.item()) * bytes_per_pivot / 1e9, "unit": "GB/s", "pivots_per_s": nq / float(t2.item()),
-           "h2d_bytes_per_step": 0,
-           "d2h_bytes_per_step": int(8 * (n_total + 1)),
-           "note": "inputs generated on the device inside the timed region: a 137 GB tableau cannot be staged "
-                   "through host memory (SURVEY.md 8d); x*, z are read back to the host"}
+           "h2d_bytes_per_step": int(shard_bytes_stored * world + 4 * world * (eng.R + eng.C)) if host_T is not None else 0,
+           "d2h_bytes_per_step": int(8 * (n_total + 1) * world),
+           "pivots_per_step": int(nq), "ms_per_step": float(t2.item()) * 1e3,
+           "call": ("b200lp_attach'ed shard <- pinned host copy (H2D inside the timed region), sharded loop, "
+                    "b200lp_read_solution -> host" if host_T is not None else
+                    "shard regenerated on the device inside the timed region (host RAM cannot pin the 137 GB tableau), "
+                    "sharded loop, b200lp_read_solution -> host")}
+    if host_T is not None:
+        hk = HistoryCheck(args)
+        hk.add(eng.history(e2e_pivots))
+        e2e["history"] = hk.report()
+        if parity is not None:
+            parity["ok"] = parity["ok"] and e2e["history"].get("equals_oracle", True)
+    del host_T
     # BASELINE config 3 at N GPUs: the 100k independent 20 x 30 LPs in contiguous blocks per rank (generator blocks of
     # 1000), one warp per LP, no data-path collective; timed on the device, max over ranks
     batched = None
@@ -614,11 +890,18 @@ def _bench_sharded(args, rank, local, world):
                                   if exchange == "p2p" else "all_gather_into_tensor (NCCL)"),
                            "bytes_per_rank_per_pivot": 8 * (R + 2)},
         }
+        if parity is not None:
+            line["parity"] = parity
         if lookahead:
             line["lookahead"] = lookahead
         if batched:
             line["secondary"] = {"config3_batched_20x30": batched}
         print(json.dumps(line))
+    if parity is not None and not parity["ok"]:
+        if rank == 0:
+            print("[bench] PARITY FAILURE: the sharded GPU path differs from the oracle", file=sys.stderr)
+        dist.destroy_process_group()
+        sys.exit(3)
 
 
 def bench_batched_sharded(args, rank, local, world, solver):
@@ -694,10 +977,20 @@ def main():
     ap.add_argument("--ref-pivots", type=int, default=None,
                     help="pivots per step of the CPU reference arm (default 32 at N=1, 8 on the config-5 slab)")
     ap.add_argument("--cpu-pivots", type=int, default=384, help="pivots of the cpu_baseline sample")
+    ap.add_argument("--e2e-pivots", type=int, default=128, help="N > 1: pivots of the end-to-end step")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-secondary", dest="secondary", action="store_false")
     ap.add_argument("--no-lookahead", dest="lookahead", action="store_false")
     ap.add_argument("--exchange", default="p2p", choices=["p2p", "nccl"], help="per-pivot exchange of the sharded loops")
+    ap.add_argument("--generator", default="counter", choices=["counter", "survey"],
+                    help="N = 1 workload: the counter-based device generator shared with the sharded config (default) or "
+                         "SURVEY 8d's literal config-2 generator with seed 4, built on the host and uploaded")
+    ap.add_argument("--no-parity", dest="parity", action="store_false",
+                    help="skip the parity block (small cases against the oracle before the timed region)")
+    ap.add_argument("--no-config5-one-gpu", dest="config5_one_gpu", action="store_false",
+                    help="N = 1: skip the 137 GB config-5 tableau on one GPU (same-workload anchor of the 1 -> 8 curve)")
+    ap.add_argument("--e2e-host", default="auto", choices=["auto", "on", "off"],
+                    help="N > 1: end-to-end step from pinned HOST copies of the shards (auto: when host RAM allows)")
     args = ap.parse_args()
     world = int(os.environ.get("WORLD_SIZE", "1"))
     if world > 1:

@@ -36,7 +36,7 @@
 extern "C" {
 #endif
 
-#define B200LP_VERSION 100
+#define B200LP_VERSION 200
 
 /* entering-variable rules */
 #define B200LP_RULE_DANTZIG 0
@@ -91,6 +91,12 @@ typedef struct b200lp_opts {
     double eps_feas;        /* phase 1 ends infeasible if the sum of artificials exceeds eps_feas       */
     int32_t check_every;    /* pivots enqueued between two host reads of the device status (0: default) */
     int32_t loop_mode;      /* B200LP_LOOP_*: how the device-resident loop is driven                     */
+    double time_limit_s;    /* wall-clock bound of one b200lp_solve / _solve_dense / _run call in seconds,  */
+                            /* counted from its entry (H2D copies and tableau build included); when it    */
+                            /* expires the loop stops at the next pivot (on-chip loop) or block of pivots */
+                            /* with status LIMIT and a consistent tableau.  <= 0: no bound.  The reference */
+                            /* passes time_limit = 10 and maps the limit status to "Error"                */
+                            /* (solver_controller.py:76, :404).  Ignored by b200lp_solve_batched.         */
 } b200lp_opts;
 
 /* min c'x  s.t.  A_i x (ops_i) b_i,  x >= 0.   A is m x n row-major with row stride lda. */
@@ -133,6 +139,10 @@ int b200lp_destroy(b200lp_solver *s);
 int b200lp_set_stream(b200lp_solver *s, void *stream);
 int b200lp_use_own_stream(b200lp_solver *s);
 int b200lp_synchronize(b200lp_solver *s);
+/* Guard mode (environment B200LP_GUARD=1 when the library is first used): every buffer of the workspace lies between
+ * two 4 KB bands of a byte pattern; this counts the band bytes that were overwritten since the buffers were allocated
+ * (0 = no store left its buffer).  Test instrumentation for boxes where compute-sanitizer is not available.      */
+int b200lp_check_guards(b200lp_solver *s, int64_t *corrupted_bytes);
 
 /* ---- one LP, reference-facing (linprog seam) --------------------------------------------------------- */
 int b200lp_solve_dense(b200lp_solver *s, const b200lp_problem *p, const b200lp_opts *o, b200lp_result *r);

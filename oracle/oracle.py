@@ -91,6 +91,8 @@ def lib():
         L.orc_solve_batched.argtypes = [C.c_int64, C.c_int64, C.c_int64, _f64p, _f64p, _f64p, _i8p,
                                         C.POINTER(Opts), _i32p, _f64p, _f64p, _i32p, _i32p, C.c_int64, C.c_int32]
         L.orc_max_threads.restype = C.c_int
+        L.orc_set_threads.restype = None
+        L.orc_set_threads.argtypes = [C.c_int]
         _i64p = C.POINTER(C.c_int64)
         L.orc_full_dims.argtypes = [_f64p, _i8p, C.c_int64, C.c_int64, _i64p, _i64p]
         L.orc_full_steps.argtypes = [_f64p, C.c_int64, _f64p, _f64p, _i8p, C.c_int64, C.c_int64, C.POINTER(Opts),
@@ -282,3 +284,17 @@ def full_steps(A, b, c, ops, opts=None, cap=64):
 
 def max_threads():
     return int(lib().orc_max_threads())
+
+
+def host_cores():
+    """Cores this process may run on (its affinity mask) -- not OMP_NUM_THREADS, which launchers such as torchrun set
+    to 1 for their workers."""
+    import os
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
+def set_threads(n):
+    lib().orc_set_threads(int(n))

@@ -690,6 +690,16 @@ ORC_EXPORT int orc_full_steps(const double *A, int64_t lda, const double *b, con
     return 0;
 }
 
+/* Default team size of the parallel loops that take no explicit thread count (the generator).  torchrun exports
+ * OMP_NUM_THREADS=1 to its workers; the CPU arm of bench.py sets the team size it reports explicitly. */
+ORC_EXPORT void orc_set_threads(int n) {
+#ifdef _OPENMP
+    if (n > 0) omp_set_num_threads(n);
+#else
+    (void)n;
+#endif
+}
+
 ORC_EXPORT int orc_max_threads(void) {
 #ifdef _OPENMP
     return omp_get_max_threads();

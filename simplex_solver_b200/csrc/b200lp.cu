@@ -15,6 +15,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <chrono>
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
@@ -67,24 +68,60 @@ static int fail(int code, const char* fmt, ...) {
 // ------------------------------------------------------------------------------------------------------
 // workspace
 // ------------------------------------------------------------------------------------------------------
+// Guard mode (environment B200LP_GUARD=1, read once): every workspace buffer is allocated between two 4 KB bands
+// filled with a byte pattern, and b200lp_check_guards() counts the band bytes that no longer hold it.  It stands in for
+// compute-sanitizer's memcheck on boxes that refuse the tool: an out-of-bounds store next to any library-owned buffer
+// (pivot column copy, look-ahead history, partials, staging) shows up in the tests instead of corrupting a neighbour.
+static const size_t GUARD_BYTES = 4096;
+static const int GUARD_PATTERN = 0xA5;
+static bool guard_mode() {
+    static const bool on = [] {
+        const char* e = getenv("B200LP_GUARD");
+        return e && *e && *e != '0';
+    }();
+    return on;
+}
+
 template <typename T>
 struct DevBuf {
     T* p = nullptr;
     size_t cap = 0;  // elements
+    bool guarded = false;
+    void* base() const { return guarded ? (void*)((char*)p - GUARD_BYTES) : (void*)p; }
     int ensure(size_t n) {
         if (n <= cap) return 0;
-        if (p) cudaFree(p);
-        p = nullptr;
-        cap = 0;
-        cudaError_t e = cudaMalloc(&p, n * sizeof(T));
+        release();
+        const bool g = guard_mode();
+        const size_t payload = (n * sizeof(T) + 255) / 256 * 256;
+        void* raw = nullptr;
+        cudaError_t e = cudaMalloc(&raw, payload + (g ? 2 * GUARD_BYTES : 0));
         if (e != cudaSuccess) return fail(B200LP_E_NOMEM, "cudaMalloc(%zu bytes): %s", n * sizeof(T), cudaGetErrorString(e));
+        if (g) {
+            // (payload included: uninitialised reads become visible as pattern-valued doubles)
+            cudaMemset(raw, GUARD_PATTERN, payload + 2 * GUARD_BYTES);
+            raw = (char*)raw + GUARD_BYTES;
+        }
+        p = (T*)raw;
+        guarded = g;
         cap = n;
         return 0;
     }
+    // band bytes that were overwritten (0 when guard mode is off)
+    long long check() const {
+        if (!p || !guarded) return 0;
+        const size_t payload = (cap * sizeof(T) + 255) / 256 * 256;
+        std::vector<unsigned char> h(2 * GUARD_BYTES);
+        if (cudaMemcpy(h.data(), (char*)p - GUARD_BYTES, GUARD_BYTES, cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
+        if (cudaMemcpy(h.data() + GUARD_BYTES, (char*)p + payload, GUARD_BYTES, cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
+        long long bad = 0;
+        for (unsigned char c : h) bad += c != GUARD_PATTERN;
+        return bad;
+    }
     void release() {
-        if (p) cudaFree(p);
+        if (p) cudaFree(base());
         p = nullptr;
         cap = 0;
+        guarded = false;
     }
     DevBuf() = default;
     DevBuf(const DevBuf&) = delete;
@@ -173,7 +210,20 @@ struct b200lp_solver {
     cudaGraphExec_t graph = nullptr;
     GraphKey graph_key;
     int64_t launches = 0;
+
+    // wall-clock bound of the running call (b200lp_opts.time_limit_s): seconds on the steady clock, 0 = none
+    double deadline = 0.0;
+    double deadline_outer = 0.0;  // armed by b200lp_solve_dense so that the build counts, inherited by b200lp_solve
 };
+
+static double now_s() {
+    return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+static void arm_deadline(b200lp_solver* s, const b200lp_opts* o) {
+    if (s->deadline_outer > 0.0) s->deadline = s->deadline_outer;
+    else s->deadline = o->time_limit_s > 0.0 ? now_s() + o->time_limit_s : 0.0;
+}
+static bool deadline_passed(const b200lp_solver* s) { return s->deadline > 0.0 && now_s() >= s->deadline; }
 
 static int set_device(b200lp_solver* s) {
     CK(cudaSetDevice(s->device));
@@ -193,6 +243,7 @@ B200LP_API void b200lp_default_opts(b200lp_opts* o) {
     o->eps_feas = 1e-7;
     o->check_every = 0;
     o->loop_mode = B200LP_LOOP_AUTO;
+    o->time_limit_s = 0.0;
 }
 
 B200LP_API int b200lp_create(b200lp_solver** out, int device) {
@@ -348,6 +399,32 @@ B200LP_API int b200lp_synchronize(b200lp_solver* s) {
     if (!s) return fail(B200LP_E_INVALID, "solver is NULL");
     CKR(set_device(s));
     CK(cudaStreamSynchronize(s->stream));
+    return 0;
+}
+
+B200LP_API int b200lp_check_guards(b200lp_solver* s, int64_t* corrupted_bytes) {
+    if (!s) return fail(B200LP_E_INVALID, "solver is NULL");
+    if (!corrupted_bytes) return fail(B200LP_E_INVALID, "corrupted_bytes is NULL");
+    *corrupted_bytes = 0;
+    if (!guard_mode()) return fail(B200LP_E_STATE, "guard mode is off: set B200LP_GUARD=1 before the library is first used");
+    CKR(set_device(s));
+    CK(cudaDeviceSynchronize());
+    long long total = 0;
+    bool err = false;
+    auto add = [&](long long v) {
+        if (v < 0) err = true;
+        else total += v;
+    };
+    add(s->own_T.check()); add(s->rowlab.check()); add(s->collab.check()); add(s->col.check());
+    add(s->part_price.check()); add(s->part_ratio.check()); add(s->st.check());
+    add(s->h_row.check()); add(s->h_col.check()); add(s->h_enter.check()); add(s->h_leave.check());
+    add(s->sA.check()); add(s->sb.check()); add(s->sc.check()); add(s->sx.check()); add(s->sfun.check());
+    add(s->sinfo.check()); add(s->sops.check()); add(s->sstatus.check()); add(s->snpiv.check()); add(s->slog.check());
+    add(s->snext.check()); add(s->blk_colP.check()); add(s->blk_qP.check()); add(s->blk_obj.check());
+    add(s->blk_rhs.check()); add(s->blk_pend.check()); add(s->xbuf.check()); add(s->gbar.check());
+    add(s->part_b.check()); add(s->pk_err.check());
+    if (err) return fail(B200LP_E_CUDA, "reading a guard band failed: %s", cudaGetErrorString(cudaGetLastError()));
+    *corrupted_bytes = total;
     return 0;
 }
 
@@ -838,6 +915,8 @@ static int get_graph(b200lp_solver* s, const b200lp_opts* o, int64_t obj_row, in
     return 0;
 }
 
+static int read_state(b200lp_solver* s, DevState* out);
+
 struct OnchipPlan {
     int G = 0, stride = 0;
     size_t smem = 0;
@@ -886,17 +965,34 @@ static int run_onchip(b200lp_solver* s, const b200lp_opts* o, int64_t obj_row, c
     P.h_leave = s->h_leave.p;
     P.hist_cap = s->hist_cap;
     P.stride = plan.stride;
+    P.error = s->pk_err.p;
+    P.time_budget_ns = 0;  // the kernel runs a whole phase: it checks the wall-clock bound itself (%globaltimer)
+    if (s->deadline > 0.0) P.time_budget_ns = (long long)std::max(1.0, (s->deadline - now_s()) * 1e9);
     void* args[] = {&P};
     CK(cudaLaunchCooperativeKernel((void*)k_solve_onchip, dim3(plan.G), dim3(ONCHIP_THREADS), args, plan.smem, s->stream));
     s->launches++;
     CK(cudaMemcpyAsync(&s->st_host[0], s->st.p, sizeof(DevState), cudaMemcpyDeviceToHost, s->stream));
     CK(cudaStreamSynchronize(s->stream));
     *final_state = s->st_host[0];
+    if (final_state->status == B200LP_STATUS_NUMERICAL) {
+        int32_t err = 0;
+        CK(cudaMemcpy(&err, s->pk_err.p, sizeof(err), cudaMemcpyDeviceToHost));
+        if (err) {
+            CK(cudaMemset(s->pk_err.p, 0, sizeof(err)));
+            return fail(B200LP_E_CUDA, "on-chip loop: a grid barrier timed out");
+        }
+    }
     return 0;
 }
 
 // Runs chunks of iterations until the device reports done.  mode 0: pricing loop on obj_row; mode 1: drive-out.
 static int run_loop(b200lp_solver* s, const b200lp_opts* o, int64_t obj_row, int mode, DevState* final_state) {
+    if (deadline_passed(s)) {  // nothing is enqueued once the wall-clock bound of the call has expired
+        CKR(read_state(s, final_state));
+        final_state->done = 1;
+        final_state->status = B200LP_STATUS_LIMIT;
+        return 0;
+    }
     if (mode == 0 && o->loop_mode == B200LP_LOOP_AUTO) {
         OnchipPlan plan;
         if (onchip_plan(s, &plan)) return run_onchip(s, o, obj_row, plan, final_state);
@@ -933,7 +1029,7 @@ static int run_loop(b200lp_solver* s, const b200lp_opts* o, int64_t obj_row, int
     const int picks = s->cluster_ctas ? 1 : 2;  // launches per pick
     const int per_iter = blocked_k ? (coop ? 4 : picks * blocked_k + 4) : picks + 1 + (s->snaps ? 1 : 0);
     int slot = 0;
-    bool first = true;
+    bool first = true, timed_out = false;
     for (;;) {
         if (use_graph) {
             CK(cudaGraphLaunch(s->graph, s->stream));
@@ -953,12 +1049,20 @@ static int run_loop(b200lp_solver* s, const b200lp_opts* o, int64_t obj_row, int
             if (s->st_host[slot ^ 1].done) break;
         }
         first = false;
+        if (deadline_passed(s)) {  // whole replays only: the tableau is consistent where the loop stops
+            timed_out = true;
+            break;
+        }
         slot ^= 1;
     }
     CK(cudaStreamSynchronize(s->stream));
     // the newest copy is at least as recent as the one that reported done
     const DevState& a = s->st_host[slot];
-    *final_state = a.done ? a : s->st_host[slot ^ 1];
+    *final_state = (a.done || timed_out) ? a : s->st_host[slot ^ 1];
+    if (timed_out && !final_state->done) {
+        final_state->done = 1;
+        final_state->status = B200LP_STATUS_LIMIT;
+    }
     if (coop && final_state->status == B200LP_STATUS_NUMERICAL) {
         int32_t err = 0;
         CK(cudaMemcpy(&err, s->pk_err.p, sizeof(err), cudaMemcpyDeviceToHost));
@@ -976,7 +1080,7 @@ static int run_loop(b200lp_solver* s, const b200lp_opts* o, int64_t obj_row, int
 static int run_phase_fb(b200lp_solver* s, b200lp_opts* o, int64_t obj_row, bool is_auto, int64_t cap, int64_t* budget,
                         DevState* fin) {
     CKR(run_loop(s, o, obj_row, 0, fin));
-    if (fin->status == B200LP_STATUS_LIMIT && is_auto && o->rule == B200LP_RULE_DANTZIG) {
+    if (fin->status == B200LP_STATUS_LIMIT && is_auto && o->rule == B200LP_RULE_DANTZIG && !deadline_passed(s)) {
         o->rule = B200LP_RULE_BLAND;
         *budget += cap;
         CKR(launch_reset(s, *budget, true));
@@ -1042,6 +1146,7 @@ static int check_opts(const b200lp_opts* o) {
     if (o->update_variant < 0 || o->update_variant > 2) return fail(B200LP_E_INVALID, "unknown update variant %d", o->update_variant);
     if (o->max_pivots < 0) return fail(B200LP_E_INVALID, "max_pivots < 0");
     if (o->loop_mode < 0 || o->loop_mode > 3) return fail(B200LP_E_INVALID, "unknown loop_mode %d", o->loop_mode);
+    if (o->time_limit_s != o->time_limit_s) return fail(B200LP_E_INVALID, "time_limit_s is NaN");
     return 0;
 }
 
@@ -1050,6 +1155,7 @@ B200LP_API int b200lp_run(b200lp_solver* s, const b200lp_opts* o, int64_t obj_ro
     CKR(check_opts(o));
     if (obj_row < s->m || obj_row >= s->R) return fail(B200LP_E_INVALID, "obj_row %lld is not an objective row", (long long)obj_row);
     CKR(set_device(s));
+    arm_deadline(s, o);
     const int64_t l0 = s->launches;
     b200lp_opts oo = *o;
     const bool is_auto = o->max_pivots >= AUTO_BUDGET;
@@ -1081,6 +1187,7 @@ B200LP_API int b200lp_solve(b200lp_solver* s, const b200lp_opts* o, b200lp_resul
     if (!s || !s->T) return fail(B200LP_E_STATE, "no tableau bound");
     CKR(check_opts(o));
     CKR(set_device(s));
+    arm_deadline(s, o);
     const int64_t l0 = s->launches;
     b200lp_opts oo = *o;
     const bool is_auto = o->max_pivots >= AUTO_BUDGET;
@@ -1225,9 +1332,12 @@ B200LP_API int b200lp_solve_dense(b200lp_solver* s, const b200lp_problem* p, con
     if (!p || !r) return fail(B200LP_E_INVALID, "problem/result is NULL");
     CKR(check_opts(o));
     const int64_t l0 = s->launches;
-    CKR(b200lp_build_dense(s, p));
+    s->deadline_outer = o->time_limit_s > 0.0 ? now_s() + o->time_limit_s : 0.0;  // the copies and the build count
+    int rc = b200lp_build_dense(s, p);
     const int64_t built = s->launches - l0;
-    CKR(b200lp_solve(s, o, r));
+    if (!rc) rc = b200lp_solve(s, o, r);
+    s->deadline_outer = 0.0;
+    if (rc) return rc;
     r->kernel_launches += built;
     return 0;
 }

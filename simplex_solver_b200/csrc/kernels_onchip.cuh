@@ -49,7 +49,18 @@ struct OnchipParams {
     int32_t* h_leave;
     int64_t hist_cap;
     int32_t stride;      // odd row stride of the shared-memory slice, >= widest slice + 1
+    int32_t* error;      // set to 1 when a grid barrier times out (a CTA went missing): the host reports it
+    long long time_budget_ns;  // wall-clock bound of this launch on %globaltimer; 0 = none
 };
+
+__device__ __forceinline__ unsigned long long global_timer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+// header id of CTA 0 when the wall-clock bound has expired: every CTA reads the G headers, so all of them stop at the
+// same pivot (a time check per CTA could split the grid)
+#define ONCHIP_TIMEOUT_ID (-2.0)
 
 // Grid barrier on a monotonic arrival counter (the kernel is launched cooperatively, so all CTAs are resident).
 // One thread per CTA arrives with a release reduction (no return value to wait for) and polls with acquire loads.
@@ -70,6 +81,7 @@ __device__ __forceinline__ void grid_barrier(unsigned long long* counter, unsign
 __global__ void __launch_bounds__(ONCHIP_THREADS, 1) k_solve_onchip(const OnchipParams P) {
     extern __shared__ __align__(16) uint8_t smem_onchip[];
     __shared__ Key sk_price[ONCHIP_WARPS], sk_decide[ONCHIP_WARPS], sk_ratio[ONCHIP_WARPS];
+    __shared__ int wd_failed;  // this CTA's poll of the grid barrier gave up
     const int G = gridDim.x, g = blockIdx.x, tid = threadIdx.x;
     const int64_t R = P.R, m = P.m, C = P.C;
     const int stride = P.stride;
@@ -103,6 +115,8 @@ __global__ void __launch_bounds__(ONCHIP_THREADS, 1) k_solve_onchip(const Onchip
     // in flight: (a) the objective row, which is all the next pricing reads; (b) the column that pricing then picks, which
     // is what gets published; -- arrive at the barrier -- (c) everything else, before the wait.  Every element still
     // receives exactly one fma with the operands of DESIGN.md section 2, so the bits do not change.
+    const unsigned long long t_start = (g == 0 && tid == 0 && P.time_budget_ns > 0) ? global_timer_ns() : 0ull;
+    if (tid == 0) wd_failed = 0;
     bool pending = false;  // colbuf / qloc / pr / ps describe a pivot whose update has not been applied yet
     int pr = -1, ps = -1;  // its row and, in the CTA that owns the entering column, its local column (else -1)
 
@@ -173,6 +187,9 @@ __global__ void __launch_bounds__(ONCHIP_THREADS, 1) k_solve_onchip(const Onchip
         if (tid == 0) {
             slot[0] = mine.v;
             slot[1] = mine.lab == B200LP_NO_LAB ? -1.0 : (double)mine.lab;
+            if (g == 0 && P.time_budget_ns > 0 && (it & 15) == 0 &&
+                global_timer_ns() - t_start > (unsigned long long)P.time_budget_ns)
+                slot[1] = ONCHIP_TIMEOUT_ID;
         }
         const int cand = mine.lab != B200LP_NO_LAB ? mine.pos : -1;
         if (cand >= 0) {
@@ -202,17 +219,34 @@ __global__ void __launch_bounds__(ONCHIP_THREADS, 1) k_solve_onchip(const Onchip
         if (tid == 0) {
             const unsigned long long target = bar_round * (unsigned long long)G;
             unsigned long long v;
+            long long t0 = 0;
             do {
                 asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(P.barrier) : "memory");
+                if (v < target) {  // watchdog: a barrier that cannot complete must not hang the GPU (~2 s)
+                    if (t0 == 0) t0 = clock64();
+                    else if (clock64() - t0 > (1ll << 32)) {
+                        wd_failed = 1;
+                        *P.error = 1;
+                        break;
+                    }
+                }
             } while (v < target);
         }
         __syncthreads();
+        if (wd_failed) {
+            status = 4;
+            break;
+        }
         // ---- 4. global decision (identical on every CTA): one 16-byte header per candidate ----
         k = key_none();
         const double* xb = P.xbuf + (size_t)(it & 1) * G * xstride;
         for (int b = tid; b < G; b += ONCHIP_THREADS) {
             const double2 h = __ldcg(reinterpret_cast<const double2*>(xb + (size_t)b * xstride));
-            if (h.y >= 0.0) {
+            if (h.y == ONCHIP_TIMEOUT_ID) {  // wins under both orders: lowest id, lowest value
+                k.v = __longlong_as_double((long long)0xfff0000000000000ull);  // -inf
+                k.lab = -1;
+                k.pos = b;
+            } else if (h.y >= 0.0) {
                 Key c;
                 c.v = h.x;
                 c.lab = (int32_t)h.y;
@@ -223,6 +257,10 @@ __global__ void __launch_bounds__(ONCHIP_THREADS, 1) k_solve_onchip(const Onchip
         const Key win = P.rule ? block_key_min_all<true>(k, sk_decide) : block_key_min_all<false>(k, sk_decide);
         if (win.lab == B200LP_NO_LAB) {
             status = 0;
+            break;
+        }
+        if (win.lab < 0) {  // wall-clock bound expired (nothing is pending here: the tableau is consistent)
+            status = 1;
             break;
         }
         const double2* wcol = reinterpret_cast<const double2*>(xb + (size_t)win.pos * xstride + 2);

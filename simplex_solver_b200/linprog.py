@@ -22,7 +22,7 @@ from . import native
 
 _MESSAGES = {
     native.STATUS_OPTIMAL: "Optimization terminated successfully. (B200 tableau simplex: Optimal)",
-    native.STATUS_LIMIT: "Iteration limit reached. (B200 tableau simplex: pivot budget exhausted)",
+    native.STATUS_LIMIT: "Iteration or time limit reached. (B200 tableau simplex: pivot budget or time_limit exhausted)",
     native.STATUS_INFEASIBLE: "The problem is infeasible. (B200 tableau simplex: phase 1 optimum > 0)",
     native.STATUS_UNBOUNDED: "The problem is unbounded. (B200 tableau simplex: no leaving row)",
     native.STATUS_NUMERICAL: "Numerical difficulties encountered. (B200 tableau simplex)",
@@ -103,8 +103,9 @@ def linprog(c, A_ub=None, b_ub=None, A_eq=None, b_eq=None, bounds=None, method="
 
     `method` is accepted and ignored (the reference passes 'highs-ds').  Recognised `options`:
     "rule" ('dantzig' | 'bland', default 'dantzig'), "maxiter" (pivot budget), "eps_cost", "eps_pivot",
-    "eps_feas", "update_variant".  "presolve" and "time_limit" (what the reference passes) are accepted and
-    have no effect.
+    "eps_feas", "update_variant", and "time_limit": seconds of wall clock for the whole call (copies, tableau build
+    and both phases); when it expires the solve stops with status 1, which the reference maps to "Error" exactly as
+    it does for HiGHS's own limit (solver_controller.py:76, :404).  "presolve" is accepted and has no effect.
     """
     options = dict(options or {})
     c, A, b, ops = rows_from_linprog_args(c, A_ub, b_ub, A_eq, b_eq)
@@ -113,7 +114,8 @@ def linprog(c, A_ub=None, b_ub=None, A_eq=None, b_eq=None, bounds=None, method="
     opts = native.make_opts(rule=rule, max_pivots=options.get("maxiter"),
                             eps_cost=options.get("eps_cost", 1e-9), eps_pivot=options.get("eps_pivot", 1e-9),
                             eps_feas=options.get("eps_feas", 1e-7),
-                            update_variant=options.get("update_variant", native.UPDATE_AUTO))
+                            update_variant=options.get("update_variant", native.UPDATE_AUTO),
+                            time_limit=options.get("time_limit"))
     solver = native.thread_solver(device)
     r = solver.solve_dense(A, b, c, ops, opts, hist_cap=hist_cap)
     status = r["status"]

@@ -37,7 +37,7 @@ EXPORTS = [
     "b200lp_read_history", "b200lp_solve_batched", "b200lp_time_update", "b200lp_build_dense",
     "b200lp_set_snapshots", "b200lp_profile_loop", "b200lp_use_own_stream", "b200lp_shard_blk_begin",
     "b200lp_shard_blk_candidate", "b200lp_shard_blk_pivot", "b200lp_shard_blk_flush", "b200lp_p2p_bytes",
-    "b200lp_p2p_connect", "b200lp_shard_push", "b200lp_shard_pull",
+    "b200lp_p2p_connect", "b200lp_shard_push", "b200lp_shard_pull", "b200lp_check_guards",
 ]
 
 _f64p = C.POINTER(C.c_double)
@@ -49,7 +49,7 @@ class Opts(C.Structure):
     _fields_ = [
         ("rule", C.c_int32), ("update_variant", C.c_int32), ("max_pivots", C.c_int64),
         ("eps_cost", C.c_double), ("eps_pivot", C.c_double), ("eps_feas", C.c_double),
-        ("check_every", C.c_int32), ("loop_mode", C.c_int32),
+        ("check_every", C.c_int32), ("loop_mode", C.c_int32), ("time_limit_s", C.c_double),
     ]
 
 
@@ -110,6 +110,7 @@ def lib():
                 L.b200lp_set_stream.argtypes = [C.c_void_p, C.c_void_p]
                 L.b200lp_synchronize.argtypes = [C.c_void_p]
                 L.b200lp_use_own_stream.argtypes = [C.c_void_p]
+                L.b200lp_check_guards.argtypes = [C.c_void_p, C.POINTER(C.c_int64)]
                 L.b200lp_solve_dense.argtypes = [C.c_void_p, C.POINTER(Problem), C.POINTER(Opts), C.POINTER(Result)]
                 L.b200lp_build_dense.argtypes = [C.c_void_p, C.POINTER(Problem)]
                 L.b200lp_set_snapshots.argtypes = [C.c_void_p, C.c_void_p, C.c_int64]
@@ -160,7 +161,8 @@ def check(rc: int):
 
 
 def make_opts(rule=RULE_DANTZIG, max_pivots=None, eps_cost=1e-9, eps_pivot=1e-9, eps_feas=1e-7,
-              update_variant=UPDATE_AUTO, check_every=0, loop_mode=LOOP_AUTO, use_graph=None) -> Opts:
+              update_variant=UPDATE_AUTO, check_every=0, loop_mode=LOOP_AUTO, use_graph=None,
+              time_limit=None) -> Opts:
     o = Opts()
     lib().b200lp_default_opts(C.byref(o))
     o.rule = rule
@@ -172,6 +174,7 @@ def make_opts(rule=RULE_DANTZIG, max_pivots=None, eps_cost=1e-9, eps_pivot=1e-9,
     if use_graph is not None:  # explicit multi-kernel loop: graph replay or plain launches
         loop_mode = LOOP_GRAPH if use_graph else LOOP_LAUNCHES
     o.loop_mode = loop_mode
+    o.time_limit_s = float(time_limit) if time_limit else 0.0  # seconds of wall clock per solve call; 0 = no bound
     return o
 
 
@@ -235,6 +238,12 @@ class Solver:
 
     def synchronize(self):
         check(lib().b200lp_synchronize(self._h))
+
+    def check_guards(self) -> int:
+        """Guard mode (B200LP_GUARD=1): bytes of the bands around the workspace buffers that were overwritten."""
+        n = C.c_int64()
+        check(lib().b200lp_check_guards(self._h, C.byref(n)))
+        return int(n.value)
 
     # ---- results ------------------------------------------------------------------------------------
     @staticmethod

@@ -47,6 +47,12 @@ class CudaShardEngine:
         """Refill the shard with the synthetic LP it was created with (device-side generator)."""
         self.solver.generate(self.seed, self.n_total, self.lab0)
 
+    def initial_labels(self):
+        """Row / column labels of the freshly generated shard (host arrays): what travels with a host copy of it."""
+        rl = np.concatenate([self.n_total + np.arange(self.m, dtype=np.int32), np.array([-1], dtype=np.int32)])
+        cl = np.concatenate([self.lab0 + np.arange(self.ncols, dtype=np.int32), np.array([-1], dtype=np.int32)])
+        return rl.astype(np.int32), cl.astype(np.int32)
+
     def new_buffer(self, world):
         return self.torch.zeros(world * (self.R + 2), dtype=self.torch.float64, device=f"cuda:{self.device}")
 
@@ -144,6 +150,18 @@ class ShardedTableau:
     def columns_of(n_total: int, world: int, rank: int):
         """Structural columns [lo, hi) owned by `rank`."""
         return shard_range(n_total, world, rank, 2)
+
+    @staticmethod
+    def columns_of_tableau(cols_total: int, world: int, rank: int):
+        """Structural columns [lo, hi) of `rank` for ONE tableau of `cols_total` stored columns (RHS included), i.e.
+        n_total = cols_total - 1 structural variables whatever the number of GPUs -- the same LP, hence the same pivot
+        sequence, at every world size.  Every shard but the last stores exactly cols_total / world columns (its
+        structural slice + its RHS replica: row strides stay multiples of 16 doubles for the usual sizes); the last
+        one takes the remainder, world - 1 columns more."""
+        per = cols_total // world - 1
+        lo = rank * per
+        hi = (rank + 1) * per if rank < world - 1 else cols_total - 1
+        return lo, hi
 
     def _all_gather(self, cand):
         if self.world == 1:

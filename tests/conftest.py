@@ -3,6 +3,10 @@ import sys
 
 import pytest
 
+# Guard mode for the whole test session (read by libb200lp when it is first used): every workspace buffer lies between
+# two bands of a byte pattern and tests assert the bands stay intact (tests/test_gpu_guard_bands.py).
+os.environ.setdefault("B200LP_GUARD", "1")
+
 ROOT = os.path.abspath(os.path.join(os.path.dirname(__file__), ".."))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
@@ -48,4 +52,6 @@ def solver():
     from simplex_solver_b200 import native
     s = native.Solver(0)
     yield s
+    corrupted = s.check_guards() if os.environ.get("B200LP_GUARD", "0") not in ("", "0") else 0
     s.close()
+    assert corrupted == 0, f"{corrupted} guard-band bytes around the shared solver's buffers were overwritten"

@@ -29,15 +29,16 @@ def test_every_declared_symbol_is_exported():
 
 def test_version_and_default_opts():
     L = native.lib()
-    assert L.b200lp_version() == 100
+    assert L.b200lp_version() == 200
     o = native.make_opts()
     assert o.rule == native.RULE_DANTZIG and o.eps_cost == 1e-9 and o.eps_pivot == 1e-9 and o.eps_feas == 1e-7
-    assert o.max_pivots == 1 << 40 and o.loop_mode == native.LOOP_AUTO
+    assert o.max_pivots == 1 << 40 and o.loop_mode == native.LOOP_AUTO and o.time_limit_s == 0.0
+    assert native.make_opts(time_limit=10).time_limit_s == 10.0
 
 
 def test_struct_layouts_match_the_header():
     # sizes implied by the field lists of include/b200lp.h (LP64)
-    assert C.sizeof(native.Opts) == 4 + 4 + 8 + 3 * 8 + 4 + 4
+    assert C.sizeof(native.Opts) == 4 + 4 + 8 + 3 * 8 + 4 + 4 + 8
     assert C.sizeof(native.Problem) == 3 * 8 + 4 * 8 + 4 + 4
     assert C.sizeof(native.Result) == 4 + 4 + 8 + 8 + 8 + 8 + 8 + 4 * 8 + 8 + 8 + 8
 

@@ -274,3 +274,41 @@ def test_concurrent_cooperative_loops_from_threads():
     assert not any(t.is_alive() for t in threads), "a thread is stuck"
     assert not errors, errors[:3]
     assert len(same) == 24 and all(same)
+
+
+def test_time_limit_is_honoured_like_the_reference_maps_it(oracle):
+    """solver_controller.py:76 bounds every solve by time_limit and :404 maps the limit status (1) to "Error".  The GPU
+    path stops at the bound with status 1 and a CONSISTENT state: the pivots taken so far are the oracle's first pivots and
+    the tableau is the oracle's tableau after them -- in the look-ahead loop (2000 x 3000, host check between replays) and
+    in the on-chip loop (1024 x 1024, %globaltimer check inside the persistent kernel)."""
+    import time
+    from simplex_solver_b200.solver_controller import status_text
+    for (m, n, what) in ((2000, 3000, "look-ahead loop"), (1024, 1024, "on-chip loop")):
+        A, b, c, ops, mx = W.dense_feasible_lp(n, seed=1, m=m)
+        s = native.Solver(0)
+        s.solve_dense(A, b, -c, ops)                       # warm-up (allocations, graph capture)
+        t0 = time.perf_counter()
+        full = s.solve_dense(A, b, -c, ops)
+        t_full = time.perf_counter() - t0
+        assert full["status"] == 0
+        limit = t_full / 4
+        t0 = time.perf_counter()
+        cut = s.solve_dense(A, b, -c, ops, native.make_opts(time_limit=limit), hist_cap=1 << 16)
+        t_cut = time.perf_counter() - t0
+        assert cut["status"] == native.STATUS_LIMIT, what
+        assert 0 < cut["n_pivots"] < full["n_pivots"], what
+        assert t_cut < 0.75 * t_full, f"{what}: {t_cut:.4f} s with time_limit {limit:.4f} s (unbounded solve {t_full:.4f} s)"
+        k = cut["n_pivots"]
+        ot = oracle.OracleTableau.build(A, b, -c, ops)
+        ref = ot.solve(oracle.make_opts(max_pivots=k), hist_cap=k)
+        assert np.array_equal(cut["piv_row"][:k], ref["piv_row"]) and np.array_equal(cut["enter_lab"][:k], ref["enter_lab"])
+        assert_bit_equal(s.read_tableau(), ot.T, what)
+        s.close()
+    # through the seam with the reference's own option name
+    A, b, c, ops, mx = W.dense_feasible_lp(3000, seed=1, m=2000)
+    r = linprog(-c, A_ub=A, b_ub=b, bounds=[(0, None)] * 3000, method="highs-ds",
+                options={"presolve": True, "time_limit": 0.005})
+    assert r.status == 1 and not r.success and r.x is None and status_text(r) == "Error"
+    # and the reference's real value leaves a small problem alone
+    r = linprog([-3.0, -5.0], A_ub=[[1, 0], [0, 2], [3, 2]], b_ub=[4, 12, 18], options={"presolve": True, "time_limit": 10})
+    assert r.success and abs(r.fun + 36.0) < 1e-9

@@ -531,3 +531,68 @@ def test_fuzz_family_gpu_vs_oracle_and_reference(solver, oracle, golden):
                 assert abs(got["fun"][i] - z) <= REL * max(1.0, abs(z)), it[0]
             checked += 1
     assert checked > 500
+
+
+# ---------------------------------------------------------------------------------------------------
+# full-size configs against the ORACLE itself (not only properties)
+# ---------------------------------------------------------------------------------------------------
+def test_config4_full_size_vs_oracle(solver, oracle):
+    """BASELINE config 4 at full size against the oracle: 24 Bland pivots of the 16384 x 16384 tableau -- pivot history
+    and every one of the 268 M stored doubles equal to oracle.OracleTableau's, for the rank-1 loop (both update kernels)
+    and the look-ahead loop; the history is also the head of the committed sequence bench.py checks its timed run with."""
+    import os
+    torch = _torch()
+    m = n = 16383
+    budget = 24
+    ot = oracle.OracleTableau.generate(4, m, n)
+    ref = ot.solve(oracle.make_opts(rule=oracle.RULE_BLAND, max_pivots=budget, threads=oracle.host_cores()), hist_cap=budget)
+    want = np.load(os.path.join(os.path.dirname(__file__), "golden", "pivot_history_config4.npy"))[:budget]
+    assert np.array_equal(np.stack([ref["piv_row"], ref["enter_lab"], ref["leave_lab"]], axis=1), want)
+    T, ld = _device_tableau(solver, m, 1, n + 1, n, n + m)
+    for kw in (dict(loop_mode=native.LOOP_GRAPH, update_variant=native.UPDATE_LDG),
+               dict(loop_mode=native.LOOP_GRAPH, update_variant=native.UPDATE_TMA),
+               dict(loop_mode=native.LOOP_BLOCKED, check_every=16)):
+        solver.generate(4, n, 0)
+        got = solver.run(native.make_opts(rule=native.RULE_BLAND, max_pivots=budget, **kw), hist_cap=budget)
+        assert got["n_pivots"] == budget
+        for key in ("piv_row", "piv_col", "enter_lab", "leave_lab"):
+            np.testing.assert_array_equal(got[key], ref[key], err_msg=f"{key} {kw}")
+        assert got["fun"] == ref["fun"]
+        assert_bit_equal(solver.read_tableau(), ot.T, f"config 4 tableau {kw}")
+    del T
+
+
+def test_config2_full_size_pivot_sequence_vs_oracle(solver, oracle):
+    """BASELINE config 2 at full size (1024 x 1024, Dantzig, to optimality): the GPU's default path (on-chip loop) and
+    the look-ahead loop take the oracle's ~10^4 pivots one for one and end on the oracle's tableau bits, x* and z*."""
+    A, b, c, ops, mx = W.dense_feasible_lp(1024, seed=0)
+    cmin = to_min_form(c, mx)
+    cap = 1 << 15
+    ref = oracle.solve_lp(A, b, cmin, ops, oracle.make_opts(rule=oracle.RULE_DANTZIG, threads=oracle.host_cores()), hist_cap=cap)
+    assert ref["status"] == 0 and 1000 < ref["n_pivots"] < cap
+    ot = oracle.OracleTableau.build(A, b, cmin, ops)
+    ot.solve(oracle.make_opts(rule=oracle.RULE_DANTZIG, threads=oracle.host_cores()))
+    for kw in (dict(loop_mode=native.LOOP_AUTO), dict(loop_mode=native.LOOP_BLOCKED)):
+        got = solver.solve_dense(A, b, cmin, ops, native.make_opts(rule=native.RULE_DANTZIG, **kw), hist_cap=cap)
+        assert got["status"] == 0 and got["n_pivots"] == ref["n_pivots"], kw
+        for key in ("piv_row", "piv_col", "enter_lab", "leave_lab"):
+            np.testing.assert_array_equal(got[key], ref[key], err_msg=f"{key} {kw}")
+        assert got["fun"] == ref["fun"]
+        assert_bit_equal(got["x"], ref["x"], "x*")
+        assert_bit_equal(solver.read_tableau(), ot.T, f"config 2 final tableau {kw}")
+
+
+@pytest.mark.parametrize("rule", [native.RULE_DANTZIG, native.RULE_BLAND])
+def test_config3_full_size_vs_oracle(solver, oracle, rule):
+    """BASELINE config 3 at full size: all 100 000 LPs against orc_solve_batched -- status, pivot count, the first 48
+    (row, column) pivots of every LP, z* and x* bit for bit."""
+    B = 100000
+    A, b, c, ops = W.batched_small_lps(0, B)
+    got = solver.solve_batched(A, b, c, ops, native.make_opts(rule=rule), log_cap=48)
+    ref = oracle.solve_batched(A, b, c, ops, oracle.make_opts(rule=rule), log_cap=48, threads=oracle.host_cores())
+    np.testing.assert_array_equal(got["status"], ref["status"])
+    np.testing.assert_array_equal(got["n_pivots"], ref["n_pivots"])
+    np.testing.assert_array_equal(got["piv_log"], ref["piv_log"])
+    ok = got["status"] == 0
+    assert_bit_equal(got["fun"][ok], ref["fun"][ok], "z*")
+    assert_bit_equal(got["x"][ok], ref["x"][ok], "x*")

@@ -207,3 +207,16 @@ def test_array_shapes_are_validated_before_the_c_abi():
         native.Solver.solve_batched(s, np.ones((4, 3, 2)), np.ones((4, 2)), np.ones((4, 2)), np.zeros((4, 3)), opts=object())
     with pytest.raises(ValueError):
         native.Solver.solve_batched(s, np.ones((3, 2)), np.ones(3), np.ones(2), np.zeros(3), opts=object())
+
+
+def test_tableau_shards_cover_one_lp_at_every_world_size():
+    """bench.py's config 5: ONE LP of cols_total - 1 structural variables at 1/2/4/8 GPUs; every shard but the last stores
+    exactly cols_total / world columns (slice + RHS replica), the last one world - 1 more."""
+    from simplex_solver_b200.sharded import ShardedTableau
+    for cols_total in (131072, 16384, 1024):
+        for world in (1, 2, 4, 8):
+            spans = [ShardedTableau.columns_of_tableau(cols_total, world, r) for r in range(world)]
+            assert spans[0][0] == 0 and spans[-1][1] == cols_total - 1
+            assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+            assert all(hi - lo + 1 == cols_total // world for lo, hi in spans[:-1])
+            assert spans[-1][1] - spans[-1][0] + 1 == cols_total // world + world - 1

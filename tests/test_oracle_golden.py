@@ -167,3 +167,27 @@ def test_fuzz_family_against_reference(oracle, golden):
                 assert abs(r["fun"] - z) <= REL * max(1.0, abs(z)), (k, rule)
         seen.add(st)
     assert seen == {0, 2, 3}
+
+
+def test_committed_pivot_histories_of_configs_4_and_5(oracle):
+    """bench.py compares the pivot history of its timed region with tests/golden/pivot_history_config{4,5}.npy.  The
+    files come from the oracle run on a column SLAB (make_pivot_history.py explains why that is exact under Bland);
+    here the slab method is checked against the full tableau, and the head of both files is recomputed."""
+    import os
+    here = os.path.join(os.path.dirname(__file__), "golden")
+
+    def hist(t, k):
+        r = t.solve(oracle.make_opts(rule=1, max_pivots=k, threads=4), hist_cap=k)
+        return np.stack([r["piv_row"], r["enter_lab"], r["leave_lab"]], axis=1)
+
+    # slab == full tableau while every entering id is inside the slab (small instance, 300 pivots)
+    full = hist(oracle.OracleTableau.generate(4, 400, 500), 300)
+    slab = hist(oracle.OracleTableau.generate(4, 400, 500, 0, 128), 300)
+    assert full[:, 1].max() < 128 and np.array_equal(full, slab)
+    # config 4: the FULL 16384 x 16384 tableau for the first pivots; config 5: its slab
+    h4 = np.load(os.path.join(here, "pivot_history_config4.npy"))
+    h5 = np.load(os.path.join(here, "pivot_history_config5.npy"))
+    assert h4.shape == (12288, 3) and h5.shape == (1024, 3) and h4.dtype == np.int32
+    assert np.array_equal(hist(oracle.OracleTableau.generate(4, 16383, 16383), 12), h4[:12])
+    assert np.array_equal(hist(oracle.OracleTableau.generate(4, 131071, 131071, 0, 256), 48), h5[:48])
+    assert h4[:, 1].max() < 4096 and h5[:, 1].max() < 1024   # the slabs that produced them held every entering id
