@@ -878,7 +878,9 @@ def _bench_sharded(args, rank, local, world):
     batched = None
     if args.secondary:
         batched = bench_batched_sharded(args, rank, local, world, eng.solver)
-    launches = args.steps * args.pivots * 5
+    # per pivot and rank: the fused pick kernel + the update kernel (peer-memory exchange); the all-gather exchange has
+    # price, extract, [NCCL], winner, ratio, update
+    launches = args.steps * args.pivots * (2 if exchange == "p2p" else 5)
     if rank == 0:
         line = {
             "metric": METRIC, "value": value * bytes_per_pivot / 1e9, "unit": "GB/s", "pivots_per_s": value,
@@ -886,7 +888,8 @@ def _bench_sharded(args, rank, local, world):
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": workload_config(args), "roofline": roofline,
             "cpu_baseline": None, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
-            "collective": {"op": ("peer-memory push over NVLink (k_p2p_push / k_p2p_pull, torch symmetric memory)"
+            "collective": {"op": ("peer-memory exchange inside the pick kernel: k_shard_pick stores every candidate into every "
+                                  "peer's region over NVLink and polls its own (torch symmetric memory; no collective call)"
                                   if exchange == "p2p" else "all_gather_into_tensor (NCCL)"),
                            "bytes_per_rank_per_pivot": 8 * (R + 2)},
         }

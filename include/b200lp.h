@@ -194,15 +194,19 @@ int b200lp_shard_blk_pivot(b200lp_solver *s, const b200lp_opts *o, const double 
                            int32_t rank);
 int b200lp_shard_blk_flush(b200lp_solver *s, int64_t obj_row);
 /* Peer-memory exchange: instead of handing the candidates to the caller's all-gather, every shard STORES its candidate
- * straight into an exchange region of every peer over NVLink (push = gather/replay of the column + remote stores + a
- * released generation flag, one kernel) and acquires the flags of its own region (pull).  bases[g] = device address, as
- * seen from this process, of rank g's region of b200lp_p2p_bytes(R, world) bytes (e.g. torch symmetric memory
- * buffer_ptrs); all ranks must synchronise once after b200lp_p2p_connect and before the first push.  Per pivot:
- * b200lp_shard_push then b200lp_shard_pull (which runs the ratio test and, unless lookahead, the update).            */
+ * straight into an exchange region of every peer over NVLink and acquires the generation words of its own region --
+ * inside ONE kernel per pivot decision that also prices, picks the winner and runs the ratio test (k_shard_pick).
+ * bases[g] = device address, as seen from this process, of rank g's region of b200lp_p2p_bytes(R, world) bytes (e.g.
+ * torch symmetric memory buffer_ptrs; 16-byte aligned); all ranks must synchronise once after b200lp_p2p_connect and
+ * before the first exchange.  Per pivot: b200lp_shard_fused (lookahead = 0: followed by the rank-1 update; 1: look-ahead
+ * loop between b200lp_shard_blk_begin and b200lp_shard_blk_flush).                                                   */
 int64_t b200lp_p2p_bytes(int64_t R, int32_t world);
 int b200lp_p2p_connect(b200lp_solver *s, void *const *bases, int32_t world, int32_t rank);
-int b200lp_shard_push(b200lp_solver *s, const b200lp_opts *o, int64_t obj_row, int32_t lookahead);
-int b200lp_shard_pull(b200lp_solver *s, const b200lp_opts *o, int32_t lookahead);
+int b200lp_shard_fused(b200lp_solver *s, const b200lp_opts *o, int64_t obj_row, int32_t lookahead);
+/* n shards of ONE tableau emulated on one GPU (tests): one launch, one thread-block cluster per shard, all resident, so
+ * that shards waiting for each other never sit in separate launches; shards[k] must be rank k of n, same device/stream */
+int b200lp_shard_fused_multi(b200lp_solver *const *shards, int32_t n, const b200lp_opts *o, int64_t obj_row,
+                             int32_t lookahead);
 /* synchronise and read the loop state of a sharded run */
 int b200lp_shard_state(b200lp_solver *s, int32_t *done, int32_t *status, int64_t *n_pivots);
 int b200lp_shard_reset(b200lp_solver *s, int64_t max_pivots);

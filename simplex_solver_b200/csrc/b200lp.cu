@@ -31,6 +31,7 @@
 #include "kernels_onchip.cuh"
 #include "kernels_pick.cuh"
 #include "kernels_picks.cuh"
+#include "kernels_shard.cuh"
 #include "kernels_update.cuh"
 
 using namespace b200lp;
@@ -98,7 +99,10 @@ struct DevBuf {
         if (e != cudaSuccess) return fail(B200LP_E_NOMEM, "cudaMalloc(%zu bytes): %s", n * sizeof(T), cudaGetErrorString(e));
         if (g) {
             // (payload included: uninitialised reads become visible as pattern-valued doubles)
+            // cudaMemset runs on the legacy default stream, which does not order with the solvers' non-blocking
+            // streams: it must have finished before anybody enqueues work on the new buffer
             cudaMemset(raw, GUARD_PATTERN, payload + 2 * GUARD_BYTES);
+            cudaStreamSynchronize(cudaStreamLegacy);
             raw = (char*)raw + GUARD_BYTES;
         }
         p = (T*)raw;
@@ -197,9 +201,13 @@ struct b200lp_solver {
     double* snaps = nullptr;
     int64_t snap_cap = 0;
 
-    // peer-memory exchange of the sharded loops
+    // peer-memory exchange of the sharded loops: the fused pick kernel reads its shard context from device memory
+    // (one entry in production; the single-GPU emulation passes an array of them to ONE launch)
     P2PPeers p2p;
     bool p2p_on = false;
+    DevBuf<long long> xgen;       // generation of the last completed exchange; zeroed by b200lp_p2p_connect only
+    DevBuf<ShardCtx> shard_ctx;   // what k_shard_pick reads
+    std::vector<ShardCtx> shard_ctx_host;  // last uploaded content (uploads happen only when something changed)
 
     // CTAs per cluster of the single-launch pick kernel (kernels_cluster.cuh); 0 = not available / switched off
     int cluster_ctas = 0;
@@ -279,8 +287,10 @@ B200LP_API int b200lp_create(b200lp_solver** out, int device) {
     CK(cudaFuncSetAttribute(k_blk_flush_db<FL_WC, FL_TR, FL_NP>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                             (int)FL_SMEM_BYTES));
     if (!getenv("B200LP_NO_CLUSTER")) {  // diagnostic switch: fall back to the two-launch pick (k_price + k_ratio)
-        const void* kernels[4] = {(const void*)k_pick_cluster<false, false>, (const void*)k_pick_cluster<true, false>,
-                                  (const void*)k_pick_cluster<false, true>, (const void*)k_pick_cluster<true, true>};
+        const void* kernels[8] = {(const void*)k_pick_cluster<false, false>, (const void*)k_pick_cluster<true, false>,
+                                  (const void*)k_pick_cluster<false, true>, (const void*)k_pick_cluster<true, true>,
+                                  (const void*)k_shard_pick<false, false>, (const void*)k_shard_pick<true, false>,
+                                  (const void*)k_shard_pick<false, true>, (const void*)k_shard_pick<true, true>};
         for (int nc : {16, 8}) {
             bool ok = true;
             for (const void* kf : kernels) {
@@ -422,7 +432,7 @@ B200LP_API int b200lp_check_guards(b200lp_solver* s, int64_t* corrupted_bytes) {
     add(s->sinfo.check()); add(s->sops.check()); add(s->sstatus.check()); add(s->snpiv.check()); add(s->slog.check());
     add(s->snext.check()); add(s->blk_colP.check()); add(s->blk_qP.check()); add(s->blk_obj.check());
     add(s->blk_rhs.check()); add(s->blk_pend.check()); add(s->xbuf.check()); add(s->gbar.check());
-    add(s->part_b.check()); add(s->pk_err.check());
+    add(s->part_b.check()); add(s->pk_err.check()); add(s->xgen.check()); add(s->shard_ctx.check());
     if (err) return fail(B200LP_E_CUDA, "reading a guard band failed: %s", cudaGetErrorString(cudaGetLastError()));
     *corrupted_bytes = total;
     return 0;
@@ -1575,65 +1585,151 @@ B200LP_API int b200lp_shard_blk_flush(b200lp_solver* s, int64_t obj_row) {
     return 0;
 }
 
-// ---- peer-memory exchange (replaces the caller's all-gather in the sharded loops) ----
+// ---- peer-memory exchange: one fused kernel per pivot decision (kernels_shard.cuh) ----
+static int64_t p2p_xstride(int64_t R) { return (R + 3) & ~(int64_t)1; }  // even: 16-byte stores into every record
+
 B200LP_API int64_t b200lp_p2p_bytes(int64_t R, int32_t world) {
     if (R < 1 || world < 1 || world > 16) return -1;
-    return (2 * (int64_t)world * (R + 2) + 2 * (int64_t)world) * 8;
+    return (2 * (int64_t)world * p2p_xstride(R) + 2 * (int64_t)world) * 8;
 }
 
 B200LP_API int b200lp_p2p_connect(b200lp_solver* s, void* const* bases, int32_t world, int32_t rank) {
     if (!s || !s->T) return fail(B200LP_E_STATE, "no tableau bound");
     if (!bases || world < 1 || world > 16 || rank < 0 || rank >= world) return fail(B200LP_E_INVALID, "bad peer arguments");
+    if (!s->cluster_ctas) return fail(B200LP_E_STATE, "thread-block clusters are not available: use the all-gather exchange");
     CKR(set_device(s));
     memset(&s->p2p, 0, sizeof(s->p2p));
     for (int g = 0; g < world; ++g) {
         if (!bases[g]) return fail(B200LP_E_INVALID, "peer %d has no region", g);
+        if (((uintptr_t)bases[g]) & 15) return fail(B200LP_E_INVALID, "region of peer %d is not 16-byte aligned", g);
         s->p2p.base[g] = (double*)bases[g];
     }
     s->p2p.world = world;
     s->p2p.rank = rank;
-    s->p2p.xstride = s->R + 2;
-    // own flags start at generation 0 (the caller synchronises all ranks after connect, before the first push)
+    s->p2p.xstride = p2p_xstride(s->R);
+    // own flags and the generation counter start at 0 (the caller synchronises all ranks after connect, before the
+    // first exchange); from here on the counter is never reset, whatever happens to the tableau or the loop state
+    CKR(s->xgen.ensure(1));
+    CKR(s->shard_ctx.ensure(16));
     CK(cudaMemsetAsync(s->p2p.base[rank] + 2 * (int64_t)world * s->p2p.xstride, 0, (size_t)2 * world * 8, s->stream));
-    CK(cudaMemsetAsync(&s->st.p->xgen, 0, sizeof(long long), s->stream));
-    CK(cudaMemsetAsync(&s->st.p->ticket_push, 0, sizeof(unsigned int), s->stream));
+    CK(cudaMemsetAsync(s->xgen.p, 0, sizeof(long long), s->stream));
     CK(cudaStreamSynchronize(s->stream));
+    s->shard_ctx_host.clear();
     s->p2p_on = true;
     return 0;
 }
 
-// candidate of this shard computed and stored into every peer's region (one kernel after the pricing)
-B200LP_API int b200lp_shard_push(b200lp_solver* s, const b200lp_opts* o, int64_t obj_row, int32_t lookahead) {
-    if (!s || !s->T) return fail(B200LP_E_STATE, "no tableau bound");
-    if (!s->p2p_on) return fail(B200LP_E_STATE, "b200lp_p2p_connect was not called");
-    CKR(check_opts(o));
-    CKR(set_device(s));
-    if (lookahead) CKR(launch_blk_rowprice(s, o, obj_row, true));
-    else CKR(launch_price(s, obj_row, o->rule, o->eps_cost, true));
-    const int blocks = clampi((s->R + BLK_THREADS - 1) / BLK_THREADS, 1, 2 * s->sm_count);
-    if (lookahead) k_p2p_push<true><<<blocks, BLK_THREADS, 0, s->stream>>>(s->T, s->R, s->ld, s->st.p, s->blk, s->p2p);
-    else k_p2p_push<false><<<blocks, BLK_THREADS, 0, s->stream>>>(s->T, s->R, s->ld, s->st.p, s->blk, s->p2p);
-    s->launches++;
-    CK(cudaGetLastError());
+static ShardCtx make_shard_ctx(b200lp_solver* s) {
+    ShardCtx X;
+    memset(&X, 0, sizeof(X));
+    X.A.T = s->T;
+    X.A.R = s->R;
+    X.A.m = s->m;
+    X.A.C = s->C;
+    X.A.ld = s->ld;
+    X.A.rowlab = s->rowlab.p;
+    X.A.collab = s->collab.p;
+    X.A.art_base = s->art_base;
+    X.A.st = s->st.p;
+    X.A.col = s->col.p;
+    X.A.B = s->blk;
+    X.A.h_row = s->h_row.p;
+    X.A.h_col = s->h_col.p;
+    X.A.h_enter = s->h_enter.p;
+    X.A.h_leave = s->h_leave.p;
+    X.A.hist_cap = s->hist_cap;
+    X.P = s->p2p;
+    X.xgen = s->xgen.p;
+    X.error = s->pk_err.p;
+    return X;
+}
+
+// Upload the contexts of `n` shards into ss[0]'s context array when they differ from what is there (never inside a graph
+// capture in practice: the first chunk of a run is enqueued eagerly, its capture repeats the same arguments).
+static int sync_shard_ctx(b200lp_solver* const* ss, int n) {
+    std::vector<ShardCtx> want((size_t)n);
+    for (int k = 0; k < n; ++k) want[(size_t)k] = make_shard_ctx(ss[k]);
+    b200lp_solver* s0 = ss[0];
+    if (s0->shard_ctx_host.size() == (size_t)n && memcmp(s0->shard_ctx_host.data(), want.data(), sizeof(ShardCtx) * n) == 0) return 0;
+    CKR(s0->shard_ctx.ensure((size_t)std::max(n, 16)));
+    cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+    if (s0->stream != (cudaStream_t)0) CK(cudaStreamIsCapturing(s0->stream, &cap));
+    if (cap != cudaStreamCaptureStatusNone)
+        return fail(B200LP_E_STATE, "the shard context changed inside a stream capture: run one pivot eagerly first");
+    CK(cudaStreamSynchronize(s0->stream));
+    CK(cudaMemcpy(s0->shard_ctx.p, want.data(), sizeof(ShardCtx) * n, cudaMemcpyHostToDevice));
+    s0->shard_ctx_host = want;
     return 0;
 }
 
-// wait for all candidates of this generation, decide, ratio test (+ rank-1 update unless look-ahead)
-B200LP_API int b200lp_shard_pull(b200lp_solver* s, const b200lp_opts* o, int32_t lookahead) {
+static int launch_shard_pick(b200lp_solver* s0, int n_ctx, const b200lp_opts* o, int64_t obj_row, bool lookahead) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)(s0->cluster_ctas * n_ctx));
+    cfg.blockDim = dim3(CL_THREADS);
+    cfg.stream = s0->stream;
+    cudaLaunchAttribute at[2];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = s0->cluster_ctas;
+    at[0].val.clusterDim.y = 1;
+    at[0].val.clusterDim.z = 1;
+    at[1].id = cudaLaunchAttributeCooperative;  // emulation: clusters that wait for one another must all be resident
+    at[1].val.cooperative = 1;
+    cfg.attrs = at;
+    const ShardCtx* ctxs = s0->shard_ctx.p;
+    const bool bland = o->rule == B200LP_RULE_BLAND;
+    auto launch = [&]() -> cudaError_t {
+        if (lookahead) return bland ? cudaLaunchKernelEx(&cfg, k_shard_pick<true, true>, ctxs, obj_row, o->eps_cost, o->eps_pivot)
+                                    : cudaLaunchKernelEx(&cfg, k_shard_pick<false, true>, ctxs, obj_row, o->eps_cost, o->eps_pivot);
+        return bland ? cudaLaunchKernelEx(&cfg, k_shard_pick<true, false>, ctxs, obj_row, o->eps_cost, o->eps_pivot)
+                     : cudaLaunchKernelEx(&cfg, k_shard_pick<false, false>, ctxs, obj_row, o->eps_cost, o->eps_pivot);
+    };
+    cfg.numAttrs = n_ctx > 1 ? 2 : 1;
+    cudaError_t e = launch();
+    if (e != cudaSuccess && n_ctx > 1) {  // a driver that refuses cooperative cluster launches: the clusters of a test
+        cudaGetLastError();               // (a few dozen CTAs on an idle GPU) are co-resident anyway
+        cfg.numAttrs = 1;
+        e = launch();
+    }
+    if (e != cudaSuccess) return fail(B200LP_E_CUDA, "fused shard pick launch failed: %s", cudaGetErrorString(e));
+    s0->launches++;
+    return 0;
+}
+
+static int check_shard_args(b200lp_solver* s, const b200lp_opts* o, int64_t obj_row) {
     if (!s || !s->T) return fail(B200LP_E_STATE, "no tableau bound");
     if (!s->p2p_on) return fail(B200LP_E_STATE, "b200lp_p2p_connect was not called");
-    CKR(check_opts(o));
+    if (s->p2p.xstride != p2p_xstride(s->R)) return fail(B200LP_E_STATE, "the tableau changed its row count after b200lp_p2p_connect");
+    if (obj_row < s->m || obj_row >= s->R) return fail(B200LP_E_INVALID, "obj_row %lld is not an objective row", (long long)obj_row);
+    return check_opts(o);
+}
+
+// One pivot of the sharded loop with the peer-memory exchange: fused pick (+ rank-1 update unless look-ahead)
+B200LP_API int b200lp_shard_fused(b200lp_solver* s, const b200lp_opts* o, int64_t obj_row, int32_t lookahead) {
+    CKR(check_shard_args(s, o, obj_row));
     CKR(set_device(s));
-    k_p2p_pull<<<1, 32, 0, s->stream>>>(s->st.p, s->p2p, o->rule == B200LP_RULE_BLAND);
-    s->launches++;
-    CK(cudaGetLastError());
-    const double* ext = s->p2p.base[s->p2p.rank];
-    if (lookahead) {
-        CKR(launch_blk_ratio(s, o, ext, s->p2p.xstride));
-    } else {
-        CKR(launch_ratio(s, o->eps_pivot, false, ext, s->p2p.xstride));
-        CKR(launch_update(s, o->update_variant));
+    b200lp_solver* one[1] = {s};
+    CKR(sync_shard_ctx(one, 1));
+    CKR(launch_shard_pick(s, 1, o, obj_row, lookahead != 0));
+    if (!lookahead) CKR(launch_update(s, o->update_variant));
+    return 0;
+}
+
+// Single-GPU emulation of `n` shards (tests): ONE launch runs one cluster per shard, all resident at once, so the shards'
+// waits for one another are satisfied inside the kernel.  All solvers must live on the same device and stream.
+B200LP_API int b200lp_shard_fused_multi(b200lp_solver* const* ss, int32_t n, const b200lp_opts* o, int64_t obj_row,
+                                        int32_t lookahead) {
+    if (!ss || n < 1 || n > 8) return fail(B200LP_E_INVALID, "bad shard list");
+    for (int k = 0; k < n; ++k) {
+        CKR(check_shard_args(ss[k], o, obj_row));
+        if (ss[k]->device != ss[0]->device || ss[k]->stream != ss[0]->stream)
+            return fail(B200LP_E_INVALID, "emulated shards must share one device and one stream");
+        if (ss[k]->p2p.world != n || ss[k]->p2p.rank != k) return fail(B200LP_E_INVALID, "shard %d is not rank %d of %d", k, k, (int)n);
     }
+    CKR(set_device(ss[0]));
+    CKR(sync_shard_ctx(ss, n));
+    CKR(launch_shard_pick(ss[0], n, o, obj_row, lookahead != 0));
+    if (!lookahead)
+        for (int k = 0; k < n; ++k) CKR(launch_update(ss[k], o->update_variant));
     return 0;
 }
 
@@ -1642,6 +1738,14 @@ B200LP_API int b200lp_shard_state(b200lp_solver* s, int32_t* done, int32_t* stat
     CKR(set_device(s));
     DevState st;
     CKR(read_state(s, &st));
+    if (st.done && st.status == B200LP_STATUS_NUMERICAL && s->p2p_on) {
+        int32_t err = 0;
+        CK(cudaMemcpy(&err, s->pk_err.p, sizeof(err), cudaMemcpyDeviceToHost));
+        if (err) {
+            CK(cudaMemset(s->pk_err.p, 0, sizeof(err)));
+            return fail(B200LP_E_CUDA, "peer-memory exchange: a peer's candidate never arrived (rank missing or out of step)");
+        }
+    }
     if (done) *done = st.done;
     if (status) *status = st.status;
     if (n_pivots) *n_pivots = st.n_pivots;

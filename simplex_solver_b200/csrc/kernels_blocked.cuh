@@ -625,138 +625,18 @@ __global__ void k_blk_clear(DevState* st, BlkBuffers B) {
     st->pend = 0;
 }
 
-// ---- peer-memory exchange of the sharded loops (replaces the caller's all-gather) --------------------------------
-// Every shard owns an exchange region  [parity 2][world][R + 2] doubles + [parity 2][world] 64-bit flags  that all its
-// peers can address (NVLink / NVSwitch peer memory; the host passes the peer addresses, e.g. torch symmetric memory).
-// k_p2p_push computes this shard's candidate column and STORES it -- header and column -- straight into every peer's
-// region (remote st.global over NVLink), then the last CTA releases a generation flag in every region (st.release.sys).
-// k_p2p_pull (one warp) acquires the `world` flags of its own region and takes the winner decision.  The compute step
-// (gather / replay of the column) and the transfer are one kernel; no collective call sits between the two.
+// ---- peer-memory exchange of the sharded loops (replaces the caller's all-gather; kernel in kernels_shard.cuh) ------
+// Every shard owns an exchange region  [parity 2][world][xstride] doubles + [parity 2][world] 64-bit generation words
+// that all its peers can address (NVLink / NVSwitch peer memory; the host passes the peer addresses, e.g. torch
+// symmetric memory).  A record is [reduced cost, variable id, column (R doubles)], xstride = R + 2 rounded up to even.
 struct P2PPeers {
     double* base[16];   // base[g] = rank g's region as addressed from this GPU
     int32_t world, rank;
-    int64_t xstride;    // R + 2
+    int64_t xstride;    // R + 2, rounded up to even
 };
 
 __device__ __forceinline__ unsigned long long* p2p_flags(double* region, int world, int64_t xstride) {
     return reinterpret_cast<unsigned long long*>(region + 2 * (int64_t)world * xstride);
-}
-
-template <bool LOOKAHEAD>
-__global__ void __launch_bounds__(BLK_THREADS)
-k_p2p_push(const double* __restrict__ T, int64_t R, int64_t ld, DevState* st, BlkBuffers B, P2PPeers P) {
-    __shared__ int32_t sr[BLK_KMAX], ss[BLK_KMAX];
-    __shared__ double sinv[BLK_KMAX], sq[BLK_KMAX];
-    __shared__ bool is_last;
-    if (st->done) return;
-    const int have = st->have_pivot;
-    const long long gen = st->xgen + 1;
-    const int par = (int)(gen & 1);
-    const int64_t slot = ((int64_t)par * P.world + P.rank) * P.xstride;
-    const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, nthr = (int64_t)gridDim.x * blockDim.x;
-    if (tid == 0) {
-        const double v = have ? st->best_val : 0.0, lab = have ? (double)st->enter_lab : -1.0;
-        for (int g = 0; g < P.world; ++g) {
-            P.base[g][slot] = v;
-            P.base[g][slot + 1] = lab;
-        }
-    }
-    if (have) {
-        const int s = st->s;
-        int t = 0;
-        if (LOOKAHEAD) {
-            t = (int)(st->n_pivots - B.pend->base);
-            if (threadIdx.x < t) {
-                sr[threadIdx.x] = B.pend->r[threadIdx.x];
-                ss[threadIdx.x] = B.pend->s[threadIdx.x];
-                sinv[threadIdx.x] = B.pend->inv_p[threadIdx.x];
-                sq[threadIdx.x] = B.qP[(int64_t)threadIdx.x * B.Cpad + s];
-            }
-            __syncthreads();
-        }
-        for (int64_t i = tid; i < R; i += nthr) {
-            double a = T[i * ld + s];
-            if (LOOKAHEAD)
-                a = blk_replay<false>(a, t, B.colP + i, B.Rpad, sq, sr, ss, sinv, i, s);
-            for (int g = 0; g < P.world; ++g) P.base[g][slot + 2 + i] = a;
-        }
-    }
-    // all stores of this CTA before its ticket; the last CTA publishes the generation in every region
-    __threadfence_system();
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        const unsigned int tk = atomicAdd(&st->ticket_push, 1u);
-        is_last = (tk == gridDim.x - 1);
-    }
-    __syncthreads();
-    if (!is_last) return;
-    __threadfence_system();
-    if (threadIdx.x == 0) st->ticket_push = 0;
-    if ((int)threadIdx.x < P.world) {
-        unsigned long long* f = p2p_flags(P.base[threadIdx.x], P.world, P.xstride) + (int64_t)par * P.world + P.rank;
-        asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(f), "l"((unsigned long long)gen) : "memory");
-    }
-}
-
-// One warp: wait for the `world` candidates of this generation in the local region, then decide like k_shard_winner.
-// A peer that never shows up (crashed rank) must not hang the GPU: after ~2^34 cycles (about 9 s) the loop ends with status 4.
-__global__ void k_p2p_pull(DevState* st, P2PPeers P, int bland) {
-    if (st->done) return;
-    const int lane = threadIdx.x;
-    const long long gen = st->xgen + 1;
-    const int par = (int)(gen & 1);
-    double* region = P.base[P.rank];
-    bool ok = true;
-    if (lane < P.world) {
-        const unsigned long long* f = p2p_flags(region, P.world, P.xstride) + (int64_t)par * P.world + lane;
-        const long long t0 = clock64();
-        unsigned long long v;
-        do {
-            asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(f) : "memory");
-            if (v != (unsigned long long)gen && clock64() - t0 > (1ll << 34)) {
-                ok = false;
-                break;
-            }
-        } while (v != (unsigned long long)gen);
-    }
-    ok = __all_sync(0xffffffffu, ok);
-    if (lane != 0) return;
-    if (!ok) {
-        st->done = 1;
-        st->status = 4;
-        st->have_pivot = 0;
-        return;
-    }
-    int win = -1;
-    double wv = 0.0;
-    int32_t wl = B200LP_NO_LAB;
-    for (int g = 0; g < P.world; ++g) {
-        const double* h = region + ((int64_t)par * P.world + g) * P.xstride;
-        const double v = __ldcg(h), labd = __ldcg(h + 1);
-        if (labd < 0.0) continue;
-        const int32_t lab = (int32_t)labd;
-        bool better;
-        if (win < 0) better = true;
-        else if (bland) better = lab < wl;
-        else better = v < wv || (v == wv && lab < wl);
-        if (better) {
-            win = g;
-            wv = v;
-            wl = lab;
-        }
-    }
-    st->xgen = gen;
-    if (win < 0) {
-        st->done = 1;
-        st->status = 0;
-        st->have_pivot = 0;
-        return;
-    }
-    st->have_pivot = 1;
-    st->win_rank = par * P.world + win;  // slot index inside the region: k_ratio / k_blk_ratio read column [win_rank]
-    st->enter_lab = wl;
-    st->best_val = wv;
-    if (win != P.rank) st->s = -1;
 }
 
 // Sharded look-ahead: publish this shard's candidate [reduced cost, variable id, column brought up to date].

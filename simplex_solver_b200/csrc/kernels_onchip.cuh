@@ -219,16 +219,15 @@ __global__ void __launch_bounds__(ONCHIP_THREADS, 1) k_solve_onchip(const Onchip
         if (tid == 0) {
             const unsigned long long target = bar_round * (unsigned long long)G;
             unsigned long long v;
-            long long t0 = 0;
+            unsigned int spins = 0;
             do {
                 asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(P.barrier) : "memory");
-                if (v < target) {  // watchdog: a barrier that cannot complete must not hang the GPU (~2 s)
-                    if (t0 == 0) t0 = clock64();
-                    else if (clock64() - t0 > (1ll << 32)) {
-                        wd_failed = 1;
-                        *P.error = 1;
-                        break;
-                    }
+                // watchdog: a barrier that cannot complete must not hang the GPU.  Polls are counted (an integer add per
+                // round trip to L2, ~0.4 us) rather than timed: reading the clock between polls delays the exit
+                if (v < target && ++spins > (1u << 23)) {  // a few seconds
+                    wd_failed = 1;
+                    *P.error = 1;
+                    break;
                 }
             } while (v < target);
         }

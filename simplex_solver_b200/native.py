@@ -37,7 +37,7 @@ EXPORTS = [
     "b200lp_read_history", "b200lp_solve_batched", "b200lp_time_update", "b200lp_build_dense",
     "b200lp_set_snapshots", "b200lp_profile_loop", "b200lp_use_own_stream", "b200lp_shard_blk_begin",
     "b200lp_shard_blk_candidate", "b200lp_shard_blk_pivot", "b200lp_shard_blk_flush", "b200lp_p2p_bytes",
-    "b200lp_p2p_connect", "b200lp_shard_push", "b200lp_shard_pull", "b200lp_check_guards",
+    "b200lp_p2p_connect", "b200lp_shard_fused", "b200lp_shard_fused_multi", "b200lp_check_guards",
 ]
 
 _f64p = C.POINTER(C.c_double)
@@ -136,8 +136,9 @@ def lib():
                 L.b200lp_p2p_bytes.restype = C.c_int64
                 L.b200lp_p2p_bytes.argtypes = [C.c_int64, C.c_int32]
                 L.b200lp_p2p_connect.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.c_int32, C.c_int32]
-                L.b200lp_shard_push.argtypes = [C.c_void_p, C.POINTER(Opts), C.c_int64, C.c_int32]
-                L.b200lp_shard_pull.argtypes = [C.c_void_p, C.POINTER(Opts), C.c_int32]
+                L.b200lp_shard_fused.argtypes = [C.c_void_p, C.POINTER(Opts), C.c_int64, C.c_int32]
+                L.b200lp_shard_fused_multi.argtypes = [C.POINTER(C.c_void_p), C.c_int32, C.POINTER(Opts), C.c_int64,
+                                                       C.c_int32]
                 L.b200lp_shard_state.argtypes = [C.c_void_p, C.POINTER(C.c_int32), C.POINTER(C.c_int32),
                                                  C.POINTER(C.c_int64)]
                 L.b200lp_shard_reset.argtypes = [C.c_void_p, C.c_int64]
@@ -412,11 +413,15 @@ class Solver:
         arr = (C.c_void_p * world)(*[C.c_void_p(int(b)) for b in bases])
         check(lib().b200lp_p2p_connect(self._h, arr, world, rank))
 
-    def shard_push(self, opts: Opts, obj_row: int, lookahead: bool = False):
-        check(lib().b200lp_shard_push(self._h, C.byref(opts), obj_row, 1 if lookahead else 0))
+    def shard_fused(self, opts: Opts, obj_row: int, lookahead: bool = False):
+        """One pivot with the peer-memory exchange: fused price / exchange / winner / ratio kernel (+ rank-1 update)."""
+        check(lib().b200lp_shard_fused(self._h, C.byref(opts), obj_row, 1 if lookahead else 0))
 
-    def shard_pull(self, opts: Opts, lookahead: bool = False):
-        check(lib().b200lp_shard_pull(self._h, C.byref(opts), 1 if lookahead else 0))
+    @staticmethod
+    def shard_fused_multi(solvers, opts: Opts, obj_row: int, lookahead: bool = False):
+        """The same for n shards emulated on ONE GPU: one launch, one cluster per shard (tests)."""
+        arr = (C.c_void_p * len(solvers))(*[s._h for s in solvers])
+        check(lib().b200lp_shard_fused_multi(arr, len(solvers), C.byref(opts), obj_row, 1 if lookahead else 0))
 
     def shard_state(self):
         done, status, n = C.c_int32(), C.c_int32(), C.c_int64()

@@ -88,8 +88,8 @@ class CudaShardEngine:
         else:
             self.solver.shard_pivot(opts, gathered.data_ptr(), world, rank)
 
-    # peer-memory exchange (kernels_blocked.cuh: k_p2p_push / k_p2p_pull): candidates are stored straight into every
-    # peer's region over NVLink; no collective call inside the loop
+    # peer-memory exchange (kernels_shard.cuh: k_shard_pick): candidates are stored straight into every peer's region
+    # over NVLink by the kernel that prices, decides and runs the ratio test; no collective call inside the loop
     def enable_p2p(self, world: int, rank: int, group=None, bases=None, region=None):
         """Allocate this shard's exchange region in torch symmetric memory, rendezvous, connect.  `bases`/`region` let a
         single-process test wire two engines by hand."""
@@ -109,11 +109,9 @@ class CudaShardEngine:
             import torch.distributed as dist
             dist.barrier(group=group)
 
-    def push(self, opts, lookahead: bool = False):
-        self.solver.shard_push(opts, self.m, lookahead)
-
-    def pull(self, opts, lookahead: bool = False):
-        self.solver.shard_pull(opts, lookahead)
+    def fused(self, opts, lookahead: bool = False):
+        """One pivot: the fused kernel prices, exchanges candidates over peer memory, decides and runs the ratio test."""
+        self.solver.shard_fused(opts, self.m, lookahead)
 
     # look-ahead loop (kernels_blocked.cuh): pivots are decided from O(R + C) state and applied K at a time
     def lookahead_begin(self):
@@ -174,9 +172,8 @@ class ShardedTableau:
         eng = self.engine
         p2p = getattr(eng, "p2p", False)
         for i in range(n):
-            if p2p:  # push into every peer's region over NVLink, pull from the local one: no collective call
-                eng.push(opts, lookahead > 0)
-                eng.pull(opts, lookahead > 0)
+            if p2p:  # candidates stored into every peer's region over NVLink inside the pick kernel: no collective call
+                eng.fused(opts, lookahead > 0)
             else:
                 self._all_gather(eng.candidate(opts, lookahead > 0) if lookahead else eng.candidate(opts))
                 if lookahead:
@@ -199,7 +196,7 @@ class ShardedTableau:
         eng = self.engine
         eng.reset(max_pivots)
         if getattr(eng, "p2p", False) and self.world > 1:
-            # the pull kernel gives a missing peer ~9 s before it gives up: start the ranks together
+            # the pick kernel gives a missing peer ~4 s before it gives up: start the ranks together
             import torch.distributed as dist
             dist.barrier(group=self.group)
         lookahead = int(max(0, min(lookahead, 32)))

@@ -170,12 +170,8 @@ def test_shard_exchange_regions_and_candidates_bands(oracle, n_total):
                         e.lookahead_begin()
                 stride = m + 3
                 for it in range(budget + 2):
-                    if p2p:
-                        for e in engs:
-                            e.push(opts, lookahead > 0)
-                        torch.cuda.synchronize()
-                        for e in engs:
-                            e.pull(opts, lookahead > 0)
+                    if p2p:  # ONE launch, one cluster per shard: the shards' waits for each other resolve inside the kernel
+                        native.Solver.shard_fused_multi([e.solver for e in engs], opts, m, lookahead > 0)
                     else:
                         for r, e in enumerate(engs):
                             gathered[r * stride:(r + 1) * stride].copy_(e.candidate(opts, lookahead > 0))

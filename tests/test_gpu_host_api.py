@@ -160,13 +160,15 @@ def test_cuda_shard_engine_world1_and_emulated_world2(oracle, rule, n_total):
     for lookahead in (0, 6):
         for p2p in (False, True):
             _emulated_two_shards(oracle, one, ref, opts, m, n_total, seed, budget, lookahead, p2p)
+    _emulated_two_shards(oracle, one, ref, opts, m, n_total, seed, budget, 0, True, world=3)
+    _emulated_two_shards(oracle, one, ref, opts, m, n_total, seed, budget, 9, True, world=4)
 
 
-def _emulated_two_shards(oracle, one, ref, opts, m, n_total, seed, budget, lookahead, p2p):
-    """Two shards in ONE process on one GPU.  p2p: the peer-memory exchange (push into both regions, pull from the own
-    one) with the regions wired by hand; all pushes are issued before any pull, so no kernel waits for a later one."""
+def _emulated_two_shards(oracle, one, ref, opts, m, n_total, seed, budget, lookahead, p2p, world=2):
+    """Two shards in ONE process on one GPU.  p2p: the fused pick kernel with the peer-memory exchange, the regions wired
+    by hand, both shards in ONE launch (one cluster each, b200lp_shard_fused_multi): kernels that wait for one another
+    are never separate launches on one GPU."""
     import torch
-    world = 2
     engs = []
     for r in range(world):
         lo, hi = ShardedTableau.columns_of(n_total, world, r)
@@ -183,12 +185,8 @@ def _emulated_two_shards(oracle, one, ref, opts, m, n_total, seed, budget, looka
             e.lookahead_begin()
     stride = m + 1 + 2
     for it in range(budget + 2):
-        if p2p:
-            for e in engs:
-                e.push(opts, lookahead > 0)
-            torch.cuda.synchronize()
-            for e in engs:
-                e.pull(opts, lookahead > 0)
+        if p2p:  # ONE launch, one cluster per shard: the shards' waits for each other resolve inside the kernel
+            native.Solver.shard_fused_multi([e.solver for e in engs], opts, m, lookahead > 0)
         else:
             for r, e in enumerate(engs):
                 gathered[r * stride:(r + 1) * stride].copy_(e.candidate(opts, lookahead > 0))
