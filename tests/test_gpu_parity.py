@@ -400,8 +400,16 @@ def test_redundant_equalities_and_degenerate_rows(solver, oracle):
 
 
 def test_invalid_arguments_fail_loudly(solver):
-    with pytest.raises(native.B200LPError):
+    with pytest.raises(ValueError):  # the Python host validates before the C ABI is entered
         solver.solve_dense(np.zeros((1, 1)), np.zeros(1), np.zeros(1), np.array([7], dtype=np.int8))
+    # the C ABI itself rejects the same problem (a caller that binds the library directly)
+    import ctypes as C
+    A, b, c, ops = np.zeros((1, 1)), np.zeros(1), np.zeros(1), np.array([7], dtype=np.int8)
+    prob = native.Problem(1, 1, 1, native._ptr(A), native._ptr(b), native._ptr(c), native._ptr(ops), 0, 0)
+    res, _keep = native.Solver._result(1, 0)
+    o = native.make_opts()
+    assert native.lib().b200lp_solve_dense(solver._h, C.byref(prob), C.byref(o), C.byref(res)) == -1
+    assert b"not L/G/E" in native.lib().b200lp_last_error()
     with pytest.raises(native.B200LPError):
         solver.solve_dense(np.zeros((1, 1)), np.zeros(1), np.zeros(1), np.zeros(1, dtype=np.int8),
                            native.make_opts(rule=9))
