@@ -66,6 +66,9 @@ static int fail(int code, const char* fmt, ...) {
         if (rc__) return rc__;  \
     } while (0)
 
+static const size_t BATCHED_SMEM_MAX = 200 * 1024;  // dynamic shared memory the batched kernel may opt in to
+static const int BATCHED_MAX_CHUNKS = 16;           // chunks of a host-side batch (and work counters of their launches)
+
 // ------------------------------------------------------------------------------------------------------
 // workspace
 // ------------------------------------------------------------------------------------------------------
@@ -219,6 +222,12 @@ struct b200lp_solver {
     GraphKey graph_key;
     int64_t launches = 0;
 
+    // launch plan of the batched kernel, cached per LP shape (occupancy queries cost more than a small batch)
+    struct BatchedPlan {
+        int64_t m = -1, n = -1;
+        int wpc = 1, per_sm = 0;
+    } bplan;
+
     // wall-clock bound of the running call (b200lp_opts.time_limit_s): seconds on the steady clock, 0 = none
     double deadline = 0.0;
     double deadline_outer = 0.0;  // armed by b200lp_solve_dense so that the build counts, inherited by b200lp_solve
@@ -315,6 +324,10 @@ B200LP_API int b200lp_create(b200lp_solver** out, int device) {
             }
         }
     }
+    CK(cudaFuncSetAttribute(k_solve_batched<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BATCHED_SMEM_MAX));
+    CK(cudaFuncSetAttribute(k_solve_batched<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BATCHED_SMEM_MAX));
+    CK(cudaStreamCreateWithFlags(&s->stream2, cudaStreamNonBlocking));
+    CKR(s->snext.ensure(BATCHED_MAX_CHUNKS));
     CKR(s->gbar.ensure(1));
     {   // look-ahead picks as one persistent cooperative kernel (B200LP_NO_COOP_PICKS: diagnostic switch back to one
         // k_pick_cluster launch per pick)
@@ -1793,25 +1806,31 @@ B200LP_API int b200lp_solve_batched(b200lp_solver* s, int64_t B, int64_t m, int6
     const int64_t R = m + 2;
     size_t warp_bytes = (size_t)(R * ld + R) * 8 + (size_t)(R + ld) * 4;
     warp_bytes = (warp_bytes + 15) / 16 * 16;
-    const size_t smem_max = 200 * 1024;
+    const size_t smem_max = BATCHED_SMEM_MAX;
     if (warp_bytes > smem_max)
         return fail(B200LP_E_INVALID, "LP of %lld x %lld needs %zu bytes of shared memory per warp; use b200lp_solve_dense",
                     (long long)m, (long long)n, warp_bytes);
-    CK(cudaFuncSetAttribute(k_solve_batched<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max));
-    CK(cudaFuncSetAttribute(k_solve_batched<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max));
     // warps per CTA: the warps are persistent (they draw LPs from a counter), so the CTA size only decides how many warps
-    // fit one SM's shared memory -- take the size with the most resident warps (ties: the larger CTA)
-    int wpc = 1, per_sm = 0, best_warps = 0;
-    for (int cand = 1; cand <= 8 && (size_t)cand * warp_bytes <= smem_max; ++cand) {
-        int occ = 0;
-        if (m + 2 >= 16) CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_solve_batched<4>, cand * 32, (size_t)cand * warp_bytes));
-        else CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_solve_batched<1>, cand * 32, (size_t)cand * warp_bytes));
-        if (occ * cand >= best_warps) {
-            best_warps = occ * cand;
-            wpc = cand;
-            per_sm = occ;
+    // fit one SM's shared memory -- take the size with the most resident warps (ties: the larger CTA).  The plan depends
+    // on the LP shape only and is kept: the eight occupancy queries cost as much as a small batch.
+    if (s->bplan.m != m || s->bplan.n != n) {
+        int wpc_best = 1, per_sm_best = 0, best_warps = 0;
+        for (int cand = 1; cand <= 8 && (size_t)cand * warp_bytes <= smem_max; ++cand) {
+            int occ = 0;
+            if (m + 2 >= 16) CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_solve_batched<4>, cand * 32, (size_t)cand * warp_bytes));
+            else CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_solve_batched<1>, cand * 32, (size_t)cand * warp_bytes));
+            if (occ * cand >= best_warps) {
+                best_warps = occ * cand;
+                wpc_best = cand;
+                per_sm_best = occ;
+            }
         }
+        s->bplan.m = m;
+        s->bplan.n = n;
+        s->bplan.wpc = wpc_best;
+        s->bplan.per_sm = per_sm_best;
     }
+    const int wpc = s->bplan.wpc, per_sm = s->bplan.per_sm;
     const size_t smem = (size_t)wpc * warp_bytes;
 
     const double *dA = A, *db = b, *dc = c;
@@ -1853,16 +1872,18 @@ B200LP_API int b200lp_solve_batched(b200lp_solver* s, int64_t B, int64_t m, int6
 
     // Host inputs: the batch is cut into chunks that alternate between two streams, so that the H2D copy of one
     // chunk overlaps the kernel of the previous one and the D2H of the one before (PCIe is the bound of this path).
-    const int nchunk = (!on_device && B >= 16384) ? 8 : 1;
-    cudaStream_t q[2] = {s->stream, s->stream};
-    if (nchunk > 1) {
-        if (!s->stream2) CK(cudaStreamCreateWithFlags(&s->stream2, cudaStreamNonBlocking));
-        q[1] = s->stream2;
+    // Chunks are sized by BYTES (about 6 MB of input each, 2 .. 16 chunks): a rank's share of a sharded batch is small in
+    // LPs but still tens of MB, and without chunks its kernel waits for the whole upload.
+    int nchunk = 1;
+    if (!on_device) {
+        const double in_bytes = (double)B * ((double)m * n * 8 + (double)m * 9 + (double)n * 8);
+        nchunk = (int)std::max(1.0, std::min((double)BATCHED_MAX_CHUNKS, in_bytes / 6.0e6));
+        if (nchunk > B) nchunk = (int)B;
     }
+    cudaStream_t q[2] = {s->stream, nchunk > 1 ? s->stream2 : s->stream};
     // persistent warps: one grid of resident CTAs per launch, LPs drawn from a counter
     const int64_t resident_ctas = (int64_t)std::max(per_sm, 1) * s->sm_count;
-    CKR(s->snext.ensure(8));
-    CK(cudaMemsetAsync(s->snext.p, 0, 8 * sizeof(unsigned int), s->stream));
+    CK(cudaMemsetAsync(s->snext.p, 0, BATCHED_MAX_CHUNKS * sizeof(unsigned int), s->stream));
     CK(cudaEventRecord(s->ev0, s->stream));
     if (nchunk > 1) CK(cudaStreamWaitEvent(s->stream2, s->ev0, 0));
     for (int k = 0; k < nchunk; ++k) {
