@@ -1306,7 +1306,9 @@ B200LP_API int b200lp_build_dense(b200lp_solver* s, const b200lp_problem* p) {
     const int64_t n_obj = n_art > 0 ? 2 : 1;
     const int64_t C = n + n_ge + 1;
     const int64_t R = m + n_obj;
-    const int64_t ld = (C + 15) / 16 * 16;
+    // row stride: a multiple of 2 KB for tableaux that stream from HBM (a stride of 16 doubles' granularity costs the update
+    // kernels 7-8 % of the bandwidth on B200, scripts/probe_shard_shapes.py), 128 bytes for the small ones
+    const int64_t ld = C >= 4096 ? (C + 255) / 256 * 256 : (C + 15) / 16 * 16;
     std::vector<int32_t> collab((size_t)C, -1);
     for (int64_t j = 0; j < n; ++j) collab[(size_t)j] = (int32_t)j;
     for (int64_t i = 0; i < m; ++i)

@@ -26,6 +26,14 @@ from . import native
 from .batched import shard_range
 
 
+def row_stride(C: int) -> int:
+    """Row stride (doubles) for a tableau of C stored columns that the library's kernels stream at full speed.  Measured on
+    B200 with the pivot-update kernels on 131072-row shards: a stride that is a multiple of 16 doubles but not of 256
+    (65552, 32784, 16400) costs 7-8 % of the HBM bandwidth, with both the LDG and the TMA kernel; multiples of 256 doubles
+    (2 KB) run at the speed of the power-of-two strides, ragged last strip or not (scripts/probe_shard_shapes.py)."""
+    return (C + 255) // 256 * 256 if C >= 4096 else (C + 15) // 16 * 16
+
+
 class CudaShardEngine:
     """A column shard resident in HBM, driven through the C ABI."""
 
@@ -35,7 +43,7 @@ class CudaShardEngine:
         self.device = device
         self.m, self.n_total, self.lab0, self.ncols, self.seed = m, n_total, lab0, ncols, seed
         self.R, self.C = m + 1, ncols + 1
-        self.ld = (self.C + 15) // 16 * 16
+        self.ld = row_stride(self.C)
         self.T = torch.empty(self.R * self.ld, dtype=torch.float64, device=f"cuda:{device}")
         self.solver = native.Solver(device)
         self.solver.set_stream(torch.cuda.current_stream(device).cuda_stream)
