@@ -93,6 +93,30 @@ __global__ void k_rate_dfma(int iters, double* out) {
     out[blockIdx.x * blockDim.x + threadIdx.x] = s;
 }
 
+// are the DMMA and DFMA pipes independent?  Half the warps of every CTA run DMMA, the other half DFMA, each as much work
+// as in the pure kernels above: if the pipes are separate the mixed kernel takes max(t_dmma, t_dfma) / 2, not the sum / 2
+__global__ void k_rate_mixed(int iters, double* out) {
+    const bool use_mma = ((threadIdx.x >> 5) & 1) == 0;
+    const double a = 1.0 + threadIdx.x * 1e-9, b = 1.0 - threadIdx.x * 1e-9;
+    double s = 0;
+    if (use_mma) {
+        double d[16][2];
+        for (int t = 0; t < 16; ++t) d[t][0] = d[t][1] = threadIdx.x + t;
+        for (int i = 0; i < iters; ++i)
+#pragma unroll
+            for (int t = 0; t < 16; ++t) dmma(d[t][0], d[t][1], a, b);
+        for (int t = 0; t < 16; ++t) s += d[t][0] + d[t][1];
+    } else {
+        double d[32];
+        for (int t = 0; t < 32; ++t) d[t] = threadIdx.x + t;
+        for (int i = 0; i < iters; ++i)
+#pragma unroll
+            for (int t = 0; t < 32; ++t) d[t] = __fma_rn(a, b, d[t]);
+        for (int t = 0; t < 32; ++t) s += d[t];
+    }
+    out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
 int main() {
     unsigned long long* counts;
     cudaMallocManaged(&counts, 4 * sizeof(unsigned long long));
@@ -125,6 +149,12 @@ int main() {
         cudaEventElapsedTime(&ms, e0, e1);
         const double fma2 = 148.0 * 4 * 256 * 32.0 * iters;
         printf("DFMA       : %.2f T FMA/s (%.3f ms)\n", fma2 / (ms * 1e-3) / 1e12, ms);
+        cudaEventRecord(e0);
+        k_rate_mixed<<<148 * 4, 256>>>(iters, out);
+        cudaEventRecord(e1);
+        cudaEventSynchronize(e1);
+        cudaEventElapsedTime(&ms, e0, e1);
+        printf("mixed (4 warps DMMA + 4 warps DFMA per CTA): %.2f T FMA/s in total (%.3f ms)\n", (fma1 + fma2) / 2 / (ms * 1e-3) / 1e12, ms);
     }
     return 0;
 }
