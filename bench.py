@@ -110,6 +110,23 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def nvlink_counters(gpu_index):
+    """Sum of the NVLink data counters of one GPU in bytes (tx, rx), or None: `nvidia-smi nvlink -gt d` prints, per link,
+    "Data Tx: N KiB" / "Data Rx: N KiB".  Read before and after the timed region of the sharded bench: the difference
+    is what the peer-memory exchange moved."""
+    try:
+        out = subprocess.run(["nvidia-smi", "nvlink", "-gt", "d", "-i", str(gpu_index)], capture_output=True, text=True,
+                             timeout=20).stdout
+    except Exception:
+        return None
+    import re
+    tx = [int(v) for v in re.findall(r"Data Tx:\s*(\d+)\s*KiB", out)]
+    rx = [int(v) for v in re.findall(r"Data Rx:\s*(\d+)\s*KiB", out)]
+    if not tx and not rx:
+        return None
+    return 1024 * sum(tx), 1024 * sum(rx)
+
+
 # ----------------------------------------------------------------------------------------------------------
 # CPU arm: the oracle port on the host cores
 # ----------------------------------------------------------------------------------------------------------
@@ -739,6 +756,7 @@ def _bench_sharded(args, rank, local, world):
     torch.cuda.synchronize()
     dist.barrier()
     hist = HistoryCheck(args)
+    nvl0 = nvlink_counters(local) if rank == 0 else None
     sampler.mark()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record()
@@ -750,6 +768,7 @@ def _bench_sharded(args, rank, local, world):
     ev1.record()
     torch.cuda.synchronize()
     dist.barrier()
+    nvl1 = nvlink_counters(local) if rank == 0 else None
     clocks = sampler.stop() if rank == 0 else None
     t = torch.tensor([ev0.elapsed_time(ev1) * 1e-3], dtype=torch.float64, device=f"cuda:{local}")
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -891,7 +910,12 @@ def _bench_sharded(args, rank, local, world):
             "collective": {"op": ("peer-memory exchange inside the pick kernel: k_shard_pick stores every candidate into every "
                                   "peer's region over NVLink and polls its own (torch symmetric memory; no collective call)"
                                   if exchange == "p2p" else "all_gather_into_tensor (NCCL)"),
-                           "bytes_per_rank_per_pivot": 8 * (R + 2)},
+                           "bytes_per_rank_per_pivot": 8 * (R + 2),
+                           "algorithmic_nvlink_bytes_per_rank_per_pivot": 8 * (R + 2) * (world - 1),
+                           "nvlink_counters_rank0": None if not (nvl0 and nvl1) else {
+                               "tx_bytes_per_pivot": (nvl1[0] - nvl0[0]) / max(pivots, 1),
+                               "rx_bytes_per_pivot": (nvl1[1] - nvl0[1]) / max(pivots, 1),
+                               "source": "nvidia-smi nvlink -gt d, all links of GPU 0, difference over the timed region"}},
         }
         if parity is not None:
             line["parity"] = parity
