@@ -28,6 +28,7 @@
 #include "kernels_blocked.cuh"
 #include "kernels_build.cuh"
 #include "kernels_cluster.cuh"
+#include "kernels_flush_mma.cuh"
 #include "kernels_onchip.cuh"
 #include "kernels_pick.cuh"
 #include "kernels_picks.cuh"
@@ -213,6 +214,7 @@ struct b200lp_solver {
     std::vector<ShardCtx> shard_ctx_host;  // last uploaded content (uploads happen only when something changed)
 
     // CTAs per cluster of the single-launch pick kernel (kernels_cluster.cuh); 0 = not available / switched off
+    bool flush_dfma = false;        // look-ahead flush on the DFMA pipe (k_blk_flush_db) instead of the DMMA pipe
     int cluster_ctas = 0;
     bool coop_picks = false;        // look-ahead picks: one persistent cooperative kernel per block (kernels_picks.cuh)
     DevBuf<PickPartB> part_b;
@@ -295,6 +297,8 @@ B200LP_API int b200lp_create(b200lp_solver** out, int device) {
     CK(cudaFuncSetAttribute(k_solve_onchip, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ONCHIP_SMEM_MAX));
     CK(cudaFuncSetAttribute(k_blk_flush_db<FL_WC, FL_TR, FL_NP>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                             (int)FL_SMEM_BYTES));
+    CK(cudaFuncSetAttribute(k_blk_flush_mma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FM_SMEM_BYTES));
+    s->flush_dfma = getenv("B200LP_FLUSH_DFMA") != nullptr;  // diagnostic switch: the DFMA flush kernel instead of DMMA
     if (!getenv("B200LP_NO_CLUSTER")) {  // diagnostic switch: fall back to the two-launch pick (k_price + k_ratio)
         const void* kernels[8] = {(const void*)k_pick_cluster<false, false>, (const void*)k_pick_cluster<true, false>,
                                   (const void*)k_pick_cluster<false, true>, (const void*)k_pick_cluster<true, true>,
@@ -860,10 +864,16 @@ static int enqueue_blk_flush(b200lp_solver* s, int K, int64_t obj_row, bool row_
     // pivot rows / pivot column pairs first (general replay), then everything else (plain FMA chains)
     const unsigned sp_blocks = (unsigned)((std::max(s->R, s->C) + 255) / 256);
     k_blk_flush_special<<<dim3(sp_blocks, 2), 256, 0, s->stream>>>(s->T, s->R, s->C, s->ld, s->st.p, s->blk);
-    const int64_t sw = 64 * FL_NP * FL_WC, n_strips = (s->C + sw - 1) / sw, n_rb = (s->R + FL_TR - 1) / FL_TR;
-    const int grid = clampi(n_strips * n_rb, 1, s->sm_count);
-    k_blk_flush_db<FL_WC, FL_TR, FL_NP><<<grid, 256, FL_SMEM_BYTES, s->stream>>>(s->T, s->R, s->C, s->ld, s->st.p,
-                                                                                 s->blk, n_rb, n_strips);
+    if (s->flush_dfma) {
+        const int64_t sw = 64 * FL_NP * FL_WC, n_strips = (s->C + sw - 1) / sw, n_rb = (s->R + FL_TR - 1) / FL_TR;
+        const int grid = clampi(n_strips * n_rb, 1, s->sm_count);
+        k_blk_flush_db<FL_WC, FL_TR, FL_NP><<<grid, 256, FL_SMEM_BYTES, s->stream>>>(s->T, s->R, s->C, s->ld, s->st.p,
+                                                                                     s->blk, n_rb, n_strips);
+    } else {  // four pending steps of an 8 x 8 tile per DMMA instruction (kernels_flush_mma.cuh)
+        const int64_t n_strips = (s->C + FM_SW - 1) / FM_SW, n_rb = (s->R + FM_TR - 1) / FM_TR;
+        const int grid = clampi(n_strips * n_rb, 1, s->sm_count);
+        k_blk_flush_mma<<<grid, 256, FM_SMEM_BYTES, s->stream>>>(s->T, s->R, s->C, s->ld, s->st.p, s->blk, n_rb, n_strips);
+    }
     k_blk_clear<<<1, 1, 0, s->stream>>>(s->st.p, s->blk);
     s->launches += 3;
     (void)K;
