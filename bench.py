@@ -60,6 +60,8 @@ class ClockSampler:
         self.lines = []
 
     def start(self):
+        if os.environ.get("B200LP_BENCH_NO_SAMPLER"):  # diagnostic: is the 50 ms nvidia-smi poll visible in the timing?
+            return
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "50", "-i", str(self.gpu)],
@@ -754,9 +756,12 @@ def _bench_sharded(args, rank, local, world):
     # oracle computed for this config (tests/golden/pivot_history_config5.npy), identical at every number of GPUs
     eng.regenerate()
     torch.cuda.synchronize()
-    dist.barrier()
     hist = HistoryCheck(args)
+    # rank 0 reads the NVLink counters through nvidia-smi (tens to hundreds of ms) BEFORE the barrier that starts the
+    # timed region: read after it, the other ranks would start their clocks and then wait for rank 0 in the first exchange
     nvl0 = nvlink_counters(local) if rank == 0 else None
+    dist.barrier()
+    torch.cuda.synchronize()
     sampler.mark()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record()
@@ -764,7 +769,8 @@ def _bench_sharded(args, rank, local, world):
     for _ in range(args.steps):
         _, done_now = drv.run(opts, args.pivots, check_every=args.pivots)
         pivots += done_now
-        hist.add(eng.history(args.pivots))   # 3 x 4 x pivots bytes to the host, after the step's own status read
+        if not os.environ.get("B200LP_BENCH_NO_HISTORY"):
+            hist.add(eng.history(args.pivots))   # 3 x 4 x pivots bytes to the host, after the step's own status read
     ev1.record()
     torch.cuda.synchronize()
     dist.barrier()

@@ -214,7 +214,7 @@ struct b200lp_solver {
     std::vector<ShardCtx> shard_ctx_host;  // last uploaded content (uploads happen only when something changed)
 
     // CTAs per cluster of the single-launch pick kernel (kernels_cluster.cuh); 0 = not available / switched off
-    bool flush_dfma = false;        // look-ahead flush on the DFMA pipe (k_blk_flush_db) instead of the DMMA pipe
+    bool flush_mma = false;         // look-ahead flush through DMMA (k_blk_flush_mma) instead of the DFMA kernel
     int cluster_ctas = 0;
     bool coop_picks = false;        // look-ahead picks: one persistent cooperative kernel per block (kernels_picks.cuh)
     DevBuf<PickPartB> part_b;
@@ -298,7 +298,10 @@ B200LP_API int b200lp_create(b200lp_solver** out, int device) {
     CK(cudaFuncSetAttribute(k_blk_flush_db<FL_WC, FL_TR, FL_NP>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                             (int)FL_SMEM_BYTES));
     CK(cudaFuncSetAttribute(k_blk_flush_mma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FM_SMEM_BYTES));
-    s->flush_dfma = getenv("B200LP_FLUSH_DFMA") != nullptr;  // diagnostic switch: the DFMA flush kernel instead of DMMA
+    // diagnostic switch: the DMMA flush kernel.  Measured on B200 (scripts/probe_dmma.cu, scripts/probe_lookahead.py): every
+    // f64 mma shape compiles to DMMA.8x8x4, which peaks at 12.3 T FMA/s against 16.0 T FMA/s for DFMA and shares its units
+    // (mixed warps: 15.3 T in total), so the DMMA flush is bit-identical but slower: 23.6k vs 25.3k pivots/s at K = 32
+    s->flush_mma = getenv("B200LP_FLUSH_MMA") != nullptr;
     if (!getenv("B200LP_NO_CLUSTER")) {  // diagnostic switch: fall back to the two-launch pick (k_price + k_ratio)
         const void* kernels[8] = {(const void*)k_pick_cluster<false, false>, (const void*)k_pick_cluster<true, false>,
                                   (const void*)k_pick_cluster<false, true>, (const void*)k_pick_cluster<true, true>,
@@ -864,7 +867,7 @@ static int enqueue_blk_flush(b200lp_solver* s, int K, int64_t obj_row, bool row_
     // pivot rows / pivot column pairs first (general replay), then everything else (plain FMA chains)
     const unsigned sp_blocks = (unsigned)((std::max(s->R, s->C) + 255) / 256);
     k_blk_flush_special<<<dim3(sp_blocks, 2), 256, 0, s->stream>>>(s->T, s->R, s->C, s->ld, s->st.p, s->blk);
-    if (s->flush_dfma) {
+    if (!s->flush_mma) {
         const int64_t sw = 64 * FL_NP * FL_WC, n_strips = (s->C + sw - 1) / sw, n_rb = (s->R + FL_TR - 1) / FL_TR;
         const int grid = clampi(n_strips * n_rb, 1, s->sm_count);
         k_blk_flush_db<FL_WC, FL_TR, FL_NP><<<grid, 256, FL_SMEM_BYTES, s->stream>>>(s->T, s->R, s->C, s->ld, s->st.p,

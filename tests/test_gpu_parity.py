@@ -222,6 +222,32 @@ def test_lookahead_ragged_strips_and_row_blocks(solver, oracle, shape, K):
         assert_bit_equal(solver.read_tableau(), ot.T, f"tableau, rule {rule}")
 
 
+def test_lookahead_dmma_flush_variant_bit_exact(oracle, monkeypatch):
+    """The DMMA flush (kernels_flush_mma.cuh: four pending steps of an 8 x 8 tile per mma.sync.m8n8k4.f64) is kept as a
+    diagnostic variant behind B200LP_FLUSH_MMA (the DFMA kernel is faster on B200).  Its claim -- the instruction evaluates
+    the sequential fma chain, k = 0 first -- is checked here against the oracle: ragged strips, K not a multiple of 4."""
+    monkeypatch.setenv("B200LP_FLUSH_MMA", "1")
+    s = native.Solver(0)
+    torch = _torch()
+    try:
+        for (m, n, K) in ((300, 1100, 32), (129, 513, 7), (700, 520, 13)):
+            budget = 70
+            C = n + 1
+            ld = C + (C & 1)
+            T = torch.empty((m + 1) * ld, dtype=torch.float64, device="cuda:0")
+            s.attach(T.data_ptr(), m, 1, C, ld, n, n + m, keep=T)
+            s.generate(9, n, 0)
+            got = s.run(native.make_opts(rule=native.RULE_BLAND, max_pivots=budget, loop_mode=native.LOOP_BLOCKED,
+                                         check_every=K), hist_cap=budget)
+            ot = oracle.OracleTableau.generate(9, m, n)
+            ref = ot.solve(oracle.make_opts(rule=oracle.RULE_BLAND, max_pivots=budget), hist_cap=budget)
+            assert got["n_pivots"] == ref["n_pivots"]
+            np.testing.assert_array_equal(got["piv_row"], ref["piv_row"])
+            assert_bit_equal(s.read_tableau(), ot.T, f"tableau {m}x{n} K={K}")
+    finally:
+        s.close()
+
+
 def test_config4_lookahead_equals_rank1_loop_at_full_size(solver):
     """BASELINE config 4 at full size: 70 Bland pivots through the look-ahead loop (K = 32: two full blocks and a ragged
     one) leave the 2 GB tableau bit-identical to the rank-1 graph loop's, with the same pivot sequence."""
