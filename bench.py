@@ -113,9 +113,24 @@ class ClockSampler:
 
 
 def nvlink_counters(gpu_index):
-    """Sum of the NVLink data counters of one GPU in bytes (tx, rx), or None: `nvidia-smi nvlink -gt d` prints, per link,
-    "Data Tx: N KiB" / "Data Rx: N KiB".  Read before and after the timed region of the sharded bench: the difference
-    is what the peer-memory exchange moved."""
+    """Sum of the NVLink data counters of one GPU in bytes (tx, rx, source), or None.  NVML field values first
+    (NVML_FI_DEV_NVLINK_THROUGHPUT_DATA_TX / _RX, KiB, summed over the links by the driver), else `nvidia-smi nvlink
+    -gt d` ("Data Tx: N KiB" per link).  Read before and after the timed region of the sharded bench: the difference is
+    what the peer-memory exchange moved."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(gpu_index)
+        vals = pynvml.nvmlDeviceGetFieldValues(h, [pynvml.NVML_FI_DEV_NVLINK_THROUGHPUT_DATA_TX,
+                                                   pynvml.NVML_FI_DEV_NVLINK_THROUGHPUT_DATA_RX])
+        out = []
+        for v in vals:
+            if v.nvmlReturn != 0:
+                raise RuntimeError(f"field {v.fieldId}: nvmlReturn {v.nvmlReturn}")
+            out.append(int(v.value.ullVal))
+        return 1024 * out[0], 1024 * out[1], "NVML field values NVLINK_THROUGHPUT_DATA_TX/RX (KiB, all links)"
+    except Exception:  # noqa: BLE001
+        pass
     try:
         out = subprocess.run(["nvidia-smi", "nvlink", "-gt", "d", "-i", str(gpu_index)], capture_output=True, text=True,
                              timeout=20).stdout
@@ -126,7 +141,7 @@ def nvlink_counters(gpu_index):
     rx = [int(v) for v in re.findall(r"Data Rx:\s*(\d+)\s*KiB", out)]
     if not tx and not rx:
         return None
-    return 1024 * sum(tx), 1024 * sum(rx)
+    return 1024 * sum(tx), 1024 * sum(rx), "nvidia-smi nvlink -gt d, all links"
 
 
 # ----------------------------------------------------------------------------------------------------------
@@ -921,7 +936,7 @@ def _bench_sharded(args, rank, local, world):
                            "nvlink_counters_rank0": None if not (nvl0 and nvl1) else {
                                "tx_bytes_per_pivot": (nvl1[0] - nvl0[0]) / max(pivots, 1),
                                "rx_bytes_per_pivot": (nvl1[1] - nvl0[1]) / max(pivots, 1),
-                               "source": "nvidia-smi nvlink -gt d, all links of GPU 0, difference over the timed region"}},
+                               "source": nvl1[2] + " of GPU 0, difference over the timed region"}},
         }
         if parity is not None:
             line["parity"] = parity

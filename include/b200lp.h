@@ -210,6 +210,10 @@ int b200lp_shard_fused_multi(b200lp_solver *const *shards, int32_t n, const b200
 /* synchronise and read the loop state of a sharded run */
 int b200lp_shard_state(b200lp_solver *s, int32_t *done, int32_t *status, int64_t *n_pivots);
 int b200lp_shard_reset(b200lp_solver *s, int64_t max_pivots);
+/* A number that changes whenever anything a CALLER-captured CUDA graph of b200lp_shard_* launches bakes in may have
+ * changed (workspace buffers reallocated -- e.g. the pivot history growing with max_pivots --, tableau re-attached, peer
+ * regions or snapshots re-bound).  A caller that replays such graphs keys them by it and re-captures when it moves.  */
+int b200lp_binding_epoch(b200lp_solver *s, int64_t *epoch);
 int b200lp_read_history(b200lp_solver *s, int64_t cap, int32_t *piv_row, int32_t *piv_col, int32_t *enter_lab,
                         int32_t *leave_lab, int64_t *n_out);
 

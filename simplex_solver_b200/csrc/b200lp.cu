@@ -15,6 +15,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <atomic>
 #include <chrono>
 #include <cstdarg>
 #include <cstdio>
@@ -87,6 +88,11 @@ static bool guard_mode() {
     return on;
 }
 
+// Bumped whenever a workspace buffer is (re)allocated or released, by any solver of the process: launches that a CALLER
+// captured into a CUDA graph (simplex_solver_b200/sharded.py) bake device pointers and capacities, so a cached graph is
+// only valid for the epoch it was captured in (b200lp_binding_epoch).
+static std::atomic<long long> g_alloc_epoch{0};
+
 template <typename T>
 struct DevBuf {
     T* p = nullptr;
@@ -96,6 +102,7 @@ struct DevBuf {
     int ensure(size_t n) {
         if (n <= cap) return 0;
         release();
+        g_alloc_epoch.fetch_add(1, std::memory_order_relaxed);
         const bool g = guard_mode();
         const size_t payload = (n * sizeof(T) + 255) / 256 * 256;
         void* raw = nullptr;
@@ -126,7 +133,10 @@ struct DevBuf {
         return bad;
     }
     void release() {
-        if (p) cudaFree(base());
+        if (p) {
+            cudaFree(base());
+            g_alloc_epoch.fetch_add(1, std::memory_order_relaxed);
+        }
         p = nullptr;
         cap = 0;
         guarded = false;
@@ -223,6 +233,7 @@ struct b200lp_solver {
     cudaGraphExec_t graph = nullptr;
     GraphKey graph_key;
     int64_t launches = 0;
+    long long bind_epoch = 0;     // bumped by every (re)binding of the tableau, the snapshots and the peer regions
 
     // launch plan of the batched kernel, cached per LP shape (occupancy queries cost more than a small batch)
     struct BatchedPlan {
@@ -487,6 +498,7 @@ static int bind(b200lp_solver* s, double* T, int64_t m, int64_t n_obj, int64_t C
     if (ld < C || (ld & 1)) return fail(B200LP_E_INVALID, "row stride ld=%lld must be even and >= C=%lld", (long long)ld, (long long)C);
     if (((uintptr_t)T) & 15) return fail(B200LP_E_INVALID, "tableau base must be 16-byte aligned");
     if (m + n_obj > 0x7fffffff || C > 0x7fffffff) return fail(B200LP_E_INVALID, "tableau dimensions exceed int32 positions");
+    s->bind_epoch++;
     s->T = T;
     s->m = m;
     s->n_obj = n_obj;
@@ -1384,6 +1396,7 @@ B200LP_API int b200lp_set_snapshots(b200lp_solver* s, double* snaps_dev, int64_t
     if (!s) return fail(B200LP_E_INVALID, "solver is NULL");
     s->snaps = (snaps_dev && cap > 0) ? snaps_dev : nullptr;
     s->snap_cap = s->snaps ? cap : 0;
+    s->bind_epoch++;
     drop_graph(s);  // the snapshot buffer is baked into the captured launches (and allocators hand addresses out again)
     return 0;
 }
@@ -1644,6 +1657,17 @@ B200LP_API int b200lp_p2p_connect(b200lp_solver* s, void* const* bases, int32_t 
     CK(cudaStreamSynchronize(s->stream));
     s->shard_ctx_host.clear();
     s->p2p_on = true;
+    s->bind_epoch++;
+    return 0;
+}
+
+// A number that changes whenever anything a caller-captured launch of this solver bakes in may have changed: workspace
+// buffers (re)allocated -- history arrays growing with max_pivots, look-ahead buffers, the pivot-column copy --, the
+// tableau re-attached, snapshots or peer regions re-bound.  Callers that replay their own CUDA graphs of b200lp_shard_*
+// launches key them by it (the library's own graphs are keyed by the baked values themselves, GraphKey).
+B200LP_API int b200lp_binding_epoch(b200lp_solver* s, int64_t* epoch) {
+    if (!s || !epoch) return fail(B200LP_E_INVALID, "solver or epoch is NULL");
+    *epoch = (int64_t)(g_alloc_epoch.load(std::memory_order_relaxed) + s->bind_epoch);
     return 0;
 }
 

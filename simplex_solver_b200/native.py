@@ -38,6 +38,7 @@ EXPORTS = [
     "b200lp_set_snapshots", "b200lp_profile_loop", "b200lp_use_own_stream", "b200lp_shard_blk_begin",
     "b200lp_shard_blk_candidate", "b200lp_shard_blk_pivot", "b200lp_shard_blk_flush", "b200lp_p2p_bytes",
     "b200lp_p2p_connect", "b200lp_shard_fused", "b200lp_shard_fused_multi", "b200lp_check_guards",
+    "b200lp_binding_epoch",
 ]
 
 _f64p = C.POINTER(C.c_double)
@@ -111,6 +112,7 @@ def lib():
                 L.b200lp_synchronize.argtypes = [C.c_void_p]
                 L.b200lp_use_own_stream.argtypes = [C.c_void_p]
                 L.b200lp_check_guards.argtypes = [C.c_void_p, C.POINTER(C.c_int64)]
+                L.b200lp_binding_epoch.argtypes = [C.c_void_p, C.POINTER(C.c_int64)]
                 L.b200lp_solve_dense.argtypes = [C.c_void_p, C.POINTER(Problem), C.POINTER(Opts), C.POINTER(Result)]
                 L.b200lp_build_dense.argtypes = [C.c_void_p, C.POINTER(Problem)]
                 L.b200lp_set_snapshots.argtypes = [C.c_void_p, C.c_void_p, C.c_int64]
@@ -386,6 +388,12 @@ class Solver:
     # ---- column shards ----------------------------------------------------------------------------------
     def shard_reset(self, max_pivots: int):
         check(lib().b200lp_shard_reset(self._h, max_pivots))
+
+    def binding_epoch(self) -> int:
+        """Changes whenever a caller-captured CUDA graph of this solver's launches may hold stale pointers / capacities."""
+        e = C.c_int64()
+        check(lib().b200lp_binding_epoch(self._h, C.byref(e)))
+        return int(e.value)
 
     def shard_candidate(self, opts: Opts, obj_row: int, cand_ptr: int):
         check(lib().b200lp_shard_candidate(self._h, C.byref(opts), obj_row, C.c_void_p(cand_ptr)))

@@ -131,6 +131,10 @@ class CudaShardEngine:
     def state(self):
         return self.solver.shard_state()
 
+    def epoch(self):
+        """Key of captured chunks: moves when the library reallocates a buffer a captured launch has baked in."""
+        return self.solver.binding_epoch()
+
     def history(self, cap):
         return self.solver.read_history(cap)
 
@@ -213,6 +217,13 @@ class ShardedTableau:
         check_every = check_every or max(1, min(max_pivots, 64))
         if lookahead:
             check_every = max(lookahead, check_every // lookahead * lookahead)  # whole blocks per chunk
+        # a captured chunk bakes device pointers and capacities (pivot history arrays sized by max_pivots, look-ahead
+        # buffers, ...): it is valid for the binding epoch it was captured in, which is read AFTER reset / begin have
+        # made their allocations.  A moved epoch drops every cached chunk (their memory may have been freed).
+        epoch = eng.epoch() if hasattr(eng, "epoch") else 0
+        if epoch != getattr(self, "_epoch", epoch):
+            self._graphs.clear()
+        self._epoch = epoch
         key = (opts.rule, opts.update_variant, opts.eps_cost, opts.eps_pivot, check_every, lookahead,
                bool(getattr(eng, "p2p", False)))
         graph = self._graphs.get(key) if use_graph else None
@@ -223,6 +234,10 @@ class ShardedTableau:
             else:
                 self._chunk(opts, check_every, lookahead)
                 if use_graph and hasattr(eng, "capture_chunk") and key not in self._graphs:
+                    if hasattr(eng, "epoch") and eng.epoch() != epoch:  # the eager chunk allocated: capture next time
+                        self._epoch = eng.epoch()
+                        self._graphs.clear()
+                        epoch = self._epoch
                     self._graphs[key] = eng.capture_chunk(lambda: self._chunk(opts, check_every, lookahead))
                     graph = self._graphs[key]
             done_total += check_every

@@ -164,6 +164,35 @@ def test_cuda_shard_engine_world1_and_emulated_world2(oracle, rule, n_total):
     _emulated_two_shards(oracle, one, ref, opts, m, n_total, seed, budget, 9, True, world=4)
 
 
+@pytest.mark.parametrize("p2p", [False, True])
+def test_shard_driver_recaptures_chunks_when_the_history_grows(oracle, p2p):
+    """A chunk captured by ShardedTableau bakes the pivot-history arrays (sized by max_pivots).  A later run with a larger
+    budget and the same chunk size reallocates them: the cached graph must not be replayed (bench.py's e2e step did
+    exactly that: 16-pivot steps, then one 128-pivot run -- its history was garbage and the old arrays were written after
+    being freed).  b200lp_binding_epoch keys the chunks."""
+    import torch
+    m, n_total, seed = 96, 300, 4
+    eng = CudaShardEngine(m, n_total, 0, n_total, seed)
+    if p2p:
+        region = torch.zeros(native.Solver.p2p_bytes(m + 1, 1) // 8, dtype=torch.float64, device="cuda:0")
+        eng.enable_p2p(1, 0, bases=[region.data_ptr()], region=region)
+    drv = ShardedTableau(eng, 1, 0)
+    e0 = eng.epoch()
+    for budget in (16, 16, 128, 16, 128):
+        eng.regenerate()
+        opts = native.make_opts(rule=native.RULE_BLAND, max_pivots=budget)
+        status, n = drv.run(opts, budget, check_every=16)
+        one = oracle.OracleTableau.generate(seed, m, n_total)
+        ref = one.solve(oracle.make_opts(rule=oracle.RULE_BLAND, max_pivots=budget), hist_cap=budget)
+        assert status == ref["status"] and n == ref["n_pivots"], budget
+        h = eng.history(budget)
+        np.testing.assert_array_equal(h["piv_row"], ref["piv_row"])
+        np.testing.assert_array_equal(h["enter_lab"], ref["enter_lab"])
+        np.testing.assert_array_equal(h["leave_lab"], ref["leave_lab"])
+        assert_bit_equal(eng.tableau(), one.T, f"tableau, budget {budget}")
+    assert eng.epoch() > e0, "growing the history must move the binding epoch"
+
+
 def _emulated_two_shards(oracle, one, ref, opts, m, n_total, seed, budget, lookahead, p2p, world=2):
     """Two shards in ONE process on one GPU.  p2p: the fused pick kernel with the peer-memory exchange, the regions wired
     by hand, both shards in ONE launch (one cluster each, b200lp_shard_fused_multi): kernels that wait for one another
