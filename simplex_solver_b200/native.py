@@ -13,7 +13,7 @@ import threading
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libb200lp.so")
+LIB_PATH = os.environ.get("B200LP_LIB") or os.path.join(_HERE, "libb200lp.so")  # B200LP_LIB: A/B builds of experiments
 CSRC = os.path.join(_HERE, "csrc")
 
 RULE_DANTZIG, RULE_BLAND = 0, 1
