@@ -76,3 +76,17 @@ def test_product_package_never_touches_the_oracle():
                 text = open(os.path.join(dirpath, f)).read()
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", text, flags=re.M), f
                 assert "liboracle" not in text, f
+
+
+def test_integration_stub_matches_the_library_structs():
+    """INTEGRATION.md shows the ctypes stub a maintainer would write; its struct fields must be the ones native.py (and
+    therefore include/b200lp.h, checked above) declares -- a field missing from b200lp_opts makes the library read past
+    the caller's struct."""
+    import re
+    from simplex_solver_b200 import native
+    text = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+    for cls, ref in (("Opts", native.Opts), ("Problem", native.Problem), ("Result", native.Result)):
+        m = re.search(r"class %s\(C\.Structure\):.*?_fields_ = \[(.*?)\]\n" % cls, text, re.S)
+        assert m, cls
+        names = re.findall(r'\("(\w+)"', m.group(1))
+        assert names == [f[0] for f in ref._fields_], (cls, names)
