@@ -224,6 +224,7 @@ struct b200lp_solver {
     std::vector<ShardCtx> shard_ctx_host;  // last uploaded content (uploads happen only when something changed)
 
     // CTAs per cluster of the single-launch pick kernel (kernels_cluster.cuh); 0 = not available / switched off
+    bool shard_la_fused = false;    // sharded look-ahead decision inside the one-cluster kernel (diagnostic)
     bool flush_mma = false;         // look-ahead flush through DMMA (k_blk_flush_mma) instead of the DFMA kernel
     int cluster_ctas = 0;
     bool coop_picks = false;        // look-ahead picks: one persistent cooperative kernel per block (kernels_picks.cuh)
@@ -313,11 +314,13 @@ B200LP_API int b200lp_create(b200lp_solver** out, int device) {
     // f64 mma shape compiles to DMMA.8x8x4, which peaks at 12.3 T FMA/s against 16.0 T FMA/s for DFMA and shares its units
     // (mixed warps: 15.3 T in total), so the DMMA flush is bit-identical but slower: 23.6k vs 25.3k pivots/s at K = 32
     s->flush_mma = getenv("B200LP_FLUSH_MMA") != nullptr;
+    s->shard_la_fused = getenv("B200LP_SHARD_LA_FUSED") != nullptr;
     if (!getenv("B200LP_NO_CLUSTER")) {  // diagnostic switch: fall back to the two-launch pick (k_price + k_ratio)
-        const void* kernels[8] = {(const void*)k_pick_cluster<false, false>, (const void*)k_pick_cluster<true, false>,
-                                  (const void*)k_pick_cluster<false, true>, (const void*)k_pick_cluster<true, true>,
-                                  (const void*)k_shard_pick<false, false>, (const void*)k_shard_pick<true, false>,
-                                  (const void*)k_shard_pick<false, true>, (const void*)k_shard_pick<true, true>};
+        const void* kernels[10] = {(const void*)k_pick_cluster<false, false>, (const void*)k_pick_cluster<true, false>,
+                                   (const void*)k_pick_cluster<false, true>, (const void*)k_pick_cluster<true, true>,
+                                   (const void*)k_shard_pick<false, false>, (const void*)k_shard_pick<true, false>,
+                                   (const void*)k_shard_pick<false, true>, (const void*)k_shard_pick<true, true>,
+                                   (const void*)k_shard_pick<false, true, true>, (const void*)k_shard_pick<true, true, true>};
         for (int nc : {16, 8}) {
             bool ok = true;
             for (const void* kf : kernels) {
@@ -1714,7 +1717,8 @@ static int sync_shard_ctx(b200lp_solver* const* ss, int n) {
     return 0;
 }
 
-static int launch_shard_pick(b200lp_solver* s0, int n_ctx, const b200lp_opts* o, int64_t obj_row, bool lookahead) {
+static int launch_shard_pick(b200lp_solver* s0, int n_ctx, const b200lp_opts* o, int64_t obj_row, bool lookahead,
+                             bool pre = false) {
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)(s0->cluster_ctas * n_ctx));
     cfg.blockDim = dim3(CL_THREADS);
@@ -1730,6 +1734,9 @@ static int launch_shard_pick(b200lp_solver* s0, int n_ctx, const b200lp_opts* o,
     const ShardCtx* ctxs = s0->shard_ctx.p;
     const bool bland = o->rule == B200LP_RULE_BLAND;
     auto launch = [&]() -> cudaError_t {
+        if (lookahead && pre)
+            return bland ? cudaLaunchKernelEx(&cfg, k_shard_pick<true, true, true>, ctxs, obj_row, o->eps_cost, o->eps_pivot)
+                         : cudaLaunchKernelEx(&cfg, k_shard_pick<false, true, true>, ctxs, obj_row, o->eps_cost, o->eps_pivot);
         if (lookahead) return bland ? cudaLaunchKernelEx(&cfg, k_shard_pick<true, true>, ctxs, obj_row, o->eps_cost, o->eps_pivot)
                                     : cudaLaunchKernelEx(&cfg, k_shard_pick<false, true>, ctxs, obj_row, o->eps_cost, o->eps_pivot);
         return bland ? cudaLaunchKernelEx(&cfg, k_shard_pick<true, false>, ctxs, obj_row, o->eps_cost, o->eps_pivot)
@@ -1755,13 +1762,29 @@ static int check_shard_args(b200lp_solver* s, const b200lp_opts* o, int64_t obj_
     return check_opts(o);
 }
 
-// One pivot of the sharded loop with the peer-memory exchange: fused pick (+ rank-1 update unless look-ahead)
+// Look-ahead decision, first two launches of three: row part + pricing on all SMs (k_blk_rowprice), then the candidate
+// column gathered, replayed and pushed to every peer on all SMs (k_blk_shard_push); k_shard_pick<.., true, true> follows.
+// `ctxs` / `index`: the context array the push kernel reads and this shard's entry in it.
+static int launch_shard_push_chain(b200lp_solver* s, const b200lp_opts* o, int64_t obj_row, const ShardCtx* ctxs, int index) {
+    CKR(launch_blk_rowprice(s, o, obj_row, true));
+    const int blocks = clampi((s->R + 2 * BLK_THREADS - 1) / (2 * BLK_THREADS), 1, 2 * s->sm_count);
+    k_blk_shard_push<<<blocks, BLK_THREADS, 0, s->stream>>>(ctxs, index);
+    s->launches++;
+    CK(cudaGetLastError());
+    return 0;
+}
+
+// One pivot of the sharded loop with the peer-memory exchange.  Rank-1 loop: fused pick + update.  Look-ahead loop: the
+// decision alone, as rowprice -> push -> pick (three launches, the heavy parts on all SMs) unless the solver was
+// created with B200LP_SHARD_LA_FUSED set (diagnostic: everything inside the one-cluster kernel).
 B200LP_API int b200lp_shard_fused(b200lp_solver* s, const b200lp_opts* o, int64_t obj_row, int32_t lookahead) {
     CKR(check_shard_args(s, o, obj_row));
     CKR(set_device(s));
     b200lp_solver* one[1] = {s};
     CKR(sync_shard_ctx(one, 1));
-    CKR(launch_shard_pick(s, 1, o, obj_row, lookahead != 0));
+    const bool pre = lookahead && !s->shard_la_fused;
+    if (pre) CKR(launch_shard_push_chain(s, o, obj_row, s->shard_ctx.p, 0));
+    CKR(launch_shard_pick(s, 1, o, obj_row, lookahead != 0, pre));
     if (!lookahead) CKR(launch_update(s, o->update_variant));
     return 0;
 }
@@ -1779,7 +1802,10 @@ B200LP_API int b200lp_shard_fused_multi(b200lp_solver* const* ss, int32_t n, con
     }
     CKR(set_device(ss[0]));
     CKR(sync_shard_ctx(ss, n));
-    CKR(launch_shard_pick(ss[0], n, o, obj_row, lookahead != 0));
+    const bool pre = lookahead && !ss[0]->shard_la_fused;
+    if (pre)  // pushes wait for nobody: the shards' chains run one after the other, then ONE launch with all the clusters
+        for (int k = 0; k < n; ++k) CKR(launch_shard_push_chain(ss[k], o, obj_row, ss[0]->shard_ctx.p, k));
+    CKR(launch_shard_pick(ss[0], n, o, obj_row, lookahead != 0, pre));
     if (!lookahead)
         for (int k = 0; k < n; ++k) CKR(launch_update(ss[k], o->update_variant));
     return 0;

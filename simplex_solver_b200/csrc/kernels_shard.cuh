@@ -45,9 +45,13 @@ struct ShardCtx {
 
 constexpr int SHARD_CLUSTER = 16;
 
-template <bool BLAND, bool BLOCKED>
+// PRE (look-ahead loop only): the candidate record of this exchange has already been pushed to every peer, generation
+// word included, by k_blk_shard_push (below) right before this launch; the kernel only prices the current objective row
+// (to know its own candidate's position), waits for the peers' records, decides and runs the ratio test.
+template <bool BLAND, bool BLOCKED, bool PRE = false>
 __global__ void __launch_bounds__(CL_THREADS, 1)
 k_shard_pick(const ShardCtx* __restrict__ ctxs, int64_t obj_row, double eps_cost, double eps_pivot) {
+    static_assert(!PRE || BLOCKED, "the pre-pushed exchange belongs to the look-ahead loop");
     cg::cluster_group cluster = cg::this_cluster();
     __shared__ Key sk[CL_THREADS / 32];
     __shared__ Key slot_price, slot_ratio, bc;
@@ -162,6 +166,7 @@ k_shard_pick(const ShardCtx* __restrict__ ctxs, int64_t obj_row, double eps_cost
     const bool have = mine.lab != B200LP_NO_LAB;
     int t = 0;
     if (BLOCKED) t = (int)(n_piv - base);
+    if (!PRE) {
     if (leader) {
         const double2 h = make_double2(have ? mine.v : 0.0, have ? (double)mine.lab : -1.0);
         for (int g = 0; g < world; ++g) *reinterpret_cast<double2*>(P.base[g] + slot) = h;  // xstride is even
@@ -194,6 +199,7 @@ k_shard_pick(const ShardCtx* __restrict__ ctxs, int64_t obj_row, double eps_cost
     if (cluster.block_rank() == 0 && (int)threadIdx.x < world) {
         unsigned long long* f = p2p_flags(P.base[threadIdx.x], world, P.xstride) + (int64_t)par * world + rank;
         asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(f), "l"((unsigned long long)gen) : "memory");
+    }
     }
     // every CTA waits for the `world` generations of the local region and takes the same decision
     double* region = P.base[rank];
@@ -308,6 +314,69 @@ k_shard_pick(const ShardCtx* __restrict__ ctxs, int64_t obj_row, double eps_cost
         A.h_leave[n_piv] = leave;
     }
     st->n_pivots = n_piv + 1;
+}
+
+// Look-ahead loop, first half of the exchange on ALL SMs: the candidate column of this shard (chosen by
+// k_blk_rowprice<.., SHARDED>: DevState.have_pivot / s / enter_lab / best_val) is gathered, brought up to date by replaying
+// the pending steps and stored straight into slot `rank` of every peer's region -- the work k_shard_pick<.., BLOCKED> does
+// on one 16-CTA cluster, where the t * R * 8 bytes of history and the (world - 1) * R * 8 bytes of NVLink stores pass
+// through one GPC (52-115 us per decision on a 131072-row shard against ~15 us here).  The last CTA to finish (device
+// ticket, after a system-scope fence by every storing thread) publishes the generation word to every peer with
+// st.release.sys.  k_shard_pick<.., true, true> follows and completes the exchange.
+__global__ void __launch_bounds__(BLK_THREADS)
+k_blk_shard_push(const ShardCtx* __restrict__ ctxs, int ctx_index) {
+    __shared__ int32_t sr[BLK_KMAX], ss[BLK_KMAX];
+    __shared__ double sinv[BLK_KMAX], sq[BLK_KMAX];
+    __shared__ bool is_last;
+    const ShardCtx& X = ctxs[ctx_index];
+    const PickArgs& A = X.A;
+    const P2PPeers& P = X.P;
+    DevState* st = A.st;
+    if (st->done) return;
+    const int world = P.world, rank = P.rank;
+    const long long gen = *X.xgen + 1;
+    const int par = (int)(gen & 1);
+    const int64_t slot = ((int64_t)par * world + rank) * P.xstride;
+    const bool have = st->have_pivot != 0;
+    const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, nthr = (int64_t)gridDim.x * blockDim.x;
+    if (tid == 0) {
+        const double2 h = make_double2(have ? st->best_val : 0.0, have ? (double)st->enter_lab : -1.0);
+        for (int g = 0; g < world; ++g) *reinterpret_cast<double2*>(P.base[g] + slot) = h;
+    }
+    if (have) {
+        const int s = st->s;
+        const int t = (int)(st->n_pivots - A.B.pend->base);
+        if (threadIdx.x < t) {
+            sr[threadIdx.x] = A.B.pend->r[threadIdx.x];
+            ss[threadIdx.x] = A.B.pend->s[threadIdx.x];
+            sinv[threadIdx.x] = A.B.pend->inv_p[threadIdx.x];
+            sq[threadIdx.x] = A.B.qP[(int64_t)threadIdx.x * A.B.Cpad + s];
+        }
+        __syncthreads();
+        const int64_t R = A.R, ld = A.ld;
+        for (int64_t i = 2 * tid; i < R; i += 2 * nthr) {
+            double a0 = A.T[i * ld + s];
+            double a1 = (i + 1 < R) ? A.T[(i + 1) * ld + s] : 0.0;
+            a0 = blk_replay<false>(a0, t, A.B.colP + i, A.B.Rpad, sq, sr, ss, sinv, i, s);
+            if (i + 1 < R) a1 = blk_replay<false>(a1, t, A.B.colP + i + 1, A.B.Rpad, sq, sr, ss, sinv, i + 1, s);
+            const double2 v = make_double2(a0, a1);
+            for (int g = 0; g < world; ++g) *reinterpret_cast<double2*>(P.base[g] + slot + 2 + i) = v;
+        }
+    }
+    __threadfence_system();  // this thread's remote stores are performed before its CTA takes a ticket
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned int tk = atomicAdd(&st->ticket_push, 1u);
+        is_last = (tk == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (!is_last) return;
+    __threadfence_system();
+    if ((int)threadIdx.x < world) {
+        unsigned long long* f = p2p_flags(P.base[threadIdx.x], world, P.xstride) + (int64_t)par * world + rank;
+        asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(f), "l"((unsigned long long)gen) : "memory");
+    }
+    if (threadIdx.x == 0) st->ticket_push = 0;
 }
 
 }  // namespace b200lp
