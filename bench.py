@@ -112,6 +112,22 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+# FP64 FMA issue rate of one B200 measured on this pool with a pure DFMA kernel (scripts/probe_dmma.cu,
+# profiles/probe_dmma_r2.txt: 15.97-16.22 T FMA/s at the clock the power cap allows, ~1.69 GHz x 148 SMs x 64 FMA/clk)
+FP64_FMA_PER_S_MEASURED = 16.0e12
+
+
+def lookahead_roofline(pps, R, C, K, gpus=1):
+    """The look-ahead loop against its two roofs: the flush moves the tableau once per K pivots (2*R*C*8 bytes) and issues
+    one FP64 FMA per element and pivot (R*C per pivot), per GPU."""
+    peak, _ = measured_peak()
+    hbm = pps * 16.0 * R * C / K / gpus / 1e9
+    fma = pps * float(R) * float(C) / gpus
+    return {"hbm_GBps_per_gpu": hbm, "frac_of_hbm_peak": hbm / peak, "fp64_fma_per_s_per_gpu": fma,
+            "frac_of_fp64_peak": fma / FP64_FMA_PER_S_MEASURED,
+            "fp64_peak_source": "measured DFMA issue rate, 16.0e12 FMA/s (scripts/probe_dmma.cu)"}
+
+
 def nvlink_counters(gpu_index):
     """Sum of the NVLink data counters of one GPU in bytes (tx, rx, source), or None.  NVML field values first
     (NVML_FI_DEV_NVLINK_THROUGHPUT_DATA_TX / _RX, KiB, summed over the links by the driver), else `nvidia-smi nvlink
@@ -437,7 +453,7 @@ def _bench_single_gpu(args):
             hk.add(rb)
             lookahead[f"K={K}"] = {"pivots_per_s": pps, "speedup_vs_rank1_loop": pps / value,
                                    "hbm_bytes_per_pivot": bytes_per_pivot / K, "kernel_launches": rb["kernel_launches"],
-                                   "history": hk.report()}
+                                   "roofline": lookahead_roofline(pps, R, C, K), "history": hk.report()}
             if parity is not None:
                 parity["ok"] = parity["ok"] and lookahead[f"K={K}"]["history"].get("equals_oracle", True)
         lookahead["note"] = ("loop_mode=BLOCKED: K pivots are decided from O(R+C) state and applied in one pass over the "
@@ -845,7 +861,8 @@ def _bench_sharded(args, rank, local, world):
             hk = HistoryCheck(args)
             hk.add(eng.history(n_la))
             lookahead[f"K={K}"] = {"pivots_per_s": pps, "speedup_vs_rank1_loop": pps / value,
-                                   "hbm_bytes_per_pivot": bytes_per_pivot / K, "history": hk.report()}
+                                   "hbm_bytes_per_pivot": bytes_per_pivot / K,
+                                   "roofline": lookahead_roofline(pps, R, args.cols_total, K, world), "history": hk.report()}
             if parity is not None:
                 parity["ok"] = parity["ok"] and lookahead[f"K={K}"]["history"].get("equals_oracle", True)
 
