@@ -220,3 +220,64 @@ def test_tableau_shards_cover_one_lp_at_every_world_size():
             assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
             assert all(hi - lo + 1 == cols_total // world for lo, hi in spans[:-1])
             assert spans[-1][1] - spans[-1][0] + 1 == cols_total // world + world - 1
+
+
+def test_sharded_driver_keys_captured_chunks_by_the_binding_epoch():
+    """ShardedTableau replays a captured chunk only while the engine's binding epoch stands: a moved epoch (the library
+    reallocated something the chunk bakes in, b200lp_binding_epoch) drops every cached chunk and the next run enqueues
+    eagerly and captures again.  Stub engine, no GPU: counts eager chunks, captures and replays."""
+    from simplex_solver_b200.sharded import ShardedTableau
+
+    class Graph:
+        def __init__(self, eng):
+            self.eng = eng
+
+        def replay(self):
+            self.eng.replays += 1
+            self.eng.n += self.eng.chunk
+
+    class Engine:
+        p2p = True  # the fused path: no collective, no torch needed
+
+        def __init__(self):
+            self.eager = self.captures = self.replays = 0
+            self.n = self.budget = self.chunk = 0
+            self._epoch = 7
+            self.grow_at = None  # budget from which reset() "reallocates the history"
+
+        def new_buffer(self, world):
+            return None
+
+        def reset(self, max_pivots):
+            self.n, self.budget = 0, max_pivots
+            if self.grow_at is not None and max_pivots >= self.grow_at:
+                self._epoch += 1
+                self.grow_at = None
+
+        def epoch(self):
+            return self._epoch
+
+        def fused(self, opts, lookahead=False):
+            self.n += 1
+
+        def capture_chunk(self, body):
+            self.captures += 1
+            return Graph(self)
+
+        def state(self):
+            return self.n >= self.budget, 1, min(self.n, self.budget)
+
+    eng = Engine()
+    drv = ShardedTableau(eng, 1, 0)
+    opts = native.make_opts(max_pivots=16)
+    eng.chunk = 16
+    assert drv.run(opts, 16, check_every=16) == (1, 16)
+    assert (eng.captures, eng.replays) == (1, 0)           # first run: eager chunk, then the capture
+    assert drv.run(opts, 16, check_every=16) == (1, 16)
+    assert (eng.captures, eng.replays) == (1, 1)           # same epoch: replay
+    eng.grow_at = 128                                      # a bigger budget makes reset() reallocate
+    assert drv.run(opts, 128, check_every=16) == (1, 128)
+    assert eng.captures == 2, "the chunk must be captured again after the epoch moved"
+    replays = eng.replays
+    assert drv.run(opts, 128, check_every=16) == (1, 128)
+    assert eng.captures == 2 and eng.replays == replays + 8
