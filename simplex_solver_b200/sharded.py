@@ -180,6 +180,19 @@ class ShardedTableau:
         import torch.distributed as dist
         dist.all_gather_into_tensor(self.gathered, cand, group=self.group)
 
+    def _expired(self, deadline) -> bool:
+        """Has the wall-clock bound passed on ANY rank?  (max-reduction: all ranks must stop at the same chunk)"""
+        import time
+        late = time.monotonic() >= deadline
+        if self.world == 1:
+            return late
+        import torch
+        import torch.distributed as dist
+        dev = self.gathered.device if self.gathered is not None else "cpu"
+        flag = torch.tensor([1 if late else 0], dtype=torch.int32, device=dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MAX, group=self.group)
+        return bool(int(flag.item()))
+
     def _chunk(self, opts, n, lookahead=0):
         eng = self.engine
         p2p = getattr(eng, "p2p", False)
@@ -196,7 +209,7 @@ class ShardedTableau:
                 eng.lookahead_flush()
 
     def run(self, opts, max_pivots: int, check_every: int = 0, use_graph: bool = True, lookahead: int = 0):
-        """Enqueue pivots until optimal / unbounded / max_pivots.  Returns (status, n_pivots).
+        """Enqueue pivots until optimal / unbounded / max_pivots / opts.time_limit_s.  Returns (status, n_pivots).
 
         On GPUs the per-pivot sequence (candidate kernels -> NCCL all-gather -> winner / ratio / update kernels) of a
         whole chunk is captured once into a CUDA graph and replayed, so the host issues one launch per `check_every`
@@ -205,7 +218,10 @@ class ShardedTableau:
         lookahead = K > 0 selects the look-ahead loop: the exchange per pivot is the same, but the tableau is only
         touched once per K pivots (one flush); pivots and tableau stay bit-identical.
         """
+        import time
         eng = self.engine
+        limit = float(getattr(opts, "time_limit_s", 0.0) or 0.0)
+        deadline = time.monotonic() + limit if limit > 0.0 else None
         eng.reset(max_pivots)
         if getattr(eng, "p2p", False) and self.world > 1:
             # the pick kernel gives a missing peer ~4 s before it gives up: start the ranks together
@@ -245,4 +261,8 @@ class ShardedTableau:
             if done:
                 return status, n
             if done_total >= max_pivots + check_every:  # the device sets LIMIT itself; this is a backstop
+                return native.STATUS_LIMIT, n
+            if deadline is not None and self._expired(deadline):
+                # the wall-clock bound of the reference's solve (solver_controller.py:76), checked between chunks: every
+                # rank leaves at the same chunk (the flag is reduced over the ranks), with a consistent shard
                 return native.STATUS_LIMIT, n

@@ -102,3 +102,28 @@ def test_single_process_driver_equals_oracle():
     ref = one.solve(O.make_opts(rule=O.RULE_DANTZIG))
     assert status == ref["status"] == 0 and n == ref["n_pivots"]
     np.testing.assert_array_equal(eng.t.T, one.T)
+
+
+def _sharded_limit_worker(rank, world, port, out_dir):
+    _init(rank, world, port)
+    lo, hi = ShardedTableau.columns_of(N_TOTAL, world, rank)
+    eng = OracleShardEngine(M, N_TOTAL, lo, hi - lo, SEED)
+    drv = ShardedTableau(eng, world, rank)
+    opts = native.make_opts(rule=O.RULE_BLAND, max_pivots=BUDGET, time_limit=1e-7 if rank == 0 else 3600.0)
+    status, n = drv.run(opts, BUDGET, check_every=5)
+    np.savez(os.path.join(out_dir, f"l{rank}.npz"), status=status, n=n, hist=np.array(eng.hist))
+    dist.destroy_process_group()
+
+
+def test_sharded_driver_time_limit_stops_all_ranks_at_the_same_chunk(tmp_path):
+    """solver_controller.py:76 bounds a solve in wall-clock time and :404 maps the limit to "Error".  In the sharded driver
+    the bound is checked between chunks and reduced over the ranks: here only rank 0's clock has expired, and both ranks
+    stop after the same first chunk with status LIMIT and the oracle's first pivots."""
+    world = 2
+    mp.spawn(_sharded_limit_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    one = O.OracleTableau.generate(SEED, M, N_TOTAL)
+    ref = one.solve(O.make_opts(rule=O.RULE_BLAND, max_pivots=5), hist_cap=5)
+    for r in range(world):
+        p = np.load(tmp_path / f"l{r}.npz")
+        assert int(p["status"]) == native.STATUS_LIMIT and int(p["n"]) == 5
+        np.testing.assert_array_equal(p["hist"][:, 0], ref["piv_row"])
