@@ -832,8 +832,18 @@ def _bench_sharded(args, rank, local, world):
     upd_ms = float(tt.item())
     achieved = shard_bytes / (upd_ms * 1e-3) / 1e9
     kname = "k_update_tma" if c_loc >= 32768 else "k_update_ldg<256,8>"   # b200lp.cu: resolve_variant (AUTO)
+    # DRAM bytes per launch of the update kernel on this shard shape, from an ncu capture of one shard driven alone
+    # (profiles/update_kernel_traffic.json -> "shards"; ncu cannot run under a multi-rank command)
+    shard_traffic = None
+    try:
+        with open(os.path.join(ROOT, "profiles", "update_kernel_traffic.json")) as f:
+            ent = json.load(f).get("shards", {}).get(f"{R}x{args.cols_total // world}")
+        if ent:
+            shard_traffic = ent["dram_bytes_per_launch"]
+    except Exception:  # noqa: BLE001
+        pass
     roofline = {"bound": "hbm", "kernel": kname + " (per shard)", "achieved": achieved, "peak": peak,
-                "unit": "GB/s", "frac": achieved / peak, "peak_source": peak_src, "traffic": None,
+                "unit": "GB/s", "frac": achieved / peak, "peak_source": peak_src, "traffic": shard_traffic,
                 "algorithmic_bytes_per_launch": shard_bytes, "kernel_ms": {"update": upd_ms},
                 "loop_GBps_aggregate": value * bytes_per_pivot / 1e9,
                 "loop_frac_of_peak_per_gpu": value * bytes_per_pivot / 1e9 / world / peak,
