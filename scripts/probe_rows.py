@@ -63,6 +63,20 @@ for R in [int(x) for x in os.environ.get("PROBE_R", "16384,32768,65536,131072,26
         for vname, v in (("ldg", native.UPDATE_LDG), ("tma", native.UPDATE_TMA)):
             ms = s.time_update(1, 1, v, 5)
             out.append(f"{vname} {ms:.3f} ms = {16.0 * R * C / ms / 1e6:.0f} GB/s ({16.0 * R * C / ms / 1e6 / peak:.3f})")
+        if align is None:
+            # the yardstick at the same footprint: torch's copy of one half of the buffer onto the other (read + write
+            # bytes = the footprint, as in MEASURED_PEAKS.json's 1 Gi-element copy), best of 5
+            half = T.numel() // 2
+            a, b2 = T[:half], T[half:2 * half]
+            best = 1e9
+            for _ in range(5):
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                b2.copy_(a)
+                e1.record()
+                torch.cuda.synchronize()
+                best = min(best, e0.elapsed_time(e1))
+            out.append(f"torch copy over the same footprint {16.0 * half / best / 1e6:.0f} GB/s ({16.0 * half / best / 1e6 / peak:.3f})")
         print(f"R = {R:7d} ({nbytes / 2**30:5.1f} GiB) {name}{extra}: " + ", ".join(out), flush=True)
         if align is None:
             del T, keep
