@@ -879,9 +879,10 @@ def _bench_sharded(args, rank, local, world):
     # e2e: every rank uploads its shard of the tableau from PINNED HOST memory inside the timed region (torch copy on
     # the solver's stream into the attached device tableau), runs the step and reads x*, z back.  The host copy of the
     # shard is made once, untimed (the generator is a device kernel; 137 GB cannot come from Python lists).  The step
-    # is `e2e_pivots` pivots, more than the 16 of a device-resident step, so that the 17-69 GB upload per rank does not
-    # stand alone in the figure (a real solve of this LP takes > 10^5 pivots).  Falls back to regenerating the shard on
-    # the device -- and says so -- when the host has no room to pin the tableau.
+    # is ONE solve call with the pivot budget of the one-GPU line's solve call (`e2e_pivots` = 512; the device-resident
+    # steps above are 16 pivots only to last as long as the one-GPU step), so the upload weighs in the figure as it does
+    # at N = 1 (a real solve of this LP takes > 10^5 pivots).  Falls back to regenerating the shard on the device -- and
+    # says so -- when the host has no room to pin the tableau.
     e2e_pivots = max(args.pivots, args.e2e_pivots)
     shard_bytes_stored = 8 * eng.R * eng.ld
     host_ok = False
@@ -1054,7 +1055,8 @@ def main():
     ap.add_argument("--ref-pivots", type=int, default=None,
                     help="pivots per step of the CPU reference arm (default 32 at N=1, 8 on the config-5 slab)")
     ap.add_argument("--cpu-pivots", type=int, default=384, help="pivots of the cpu_baseline sample")
-    ap.add_argument("--e2e-pivots", type=int, default=128, help="N > 1: pivots of the end-to-end step")
+    ap.add_argument("--e2e-pivots", type=int, default=512,
+                    help="N > 1: pivot budget of the end-to-end solve call (default: the one-GPU line's 512)")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-secondary", dest="secondary", action="store_false")
     ap.add_argument("--no-lookahead", dest="lookahead", action="store_false")
