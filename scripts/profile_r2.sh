@@ -11,5 +11,6 @@ cap() { # name regex skip script args...
 cap update_ldg_r2 k_update_ldg 2 python scripts/profile_update.py ldg
 cap blk_flush_db_r2 k_blk_flush_db 1 python scripts/profile_blocked.py 32
 cap blk_picks_r2 k_blk_picks 1 python scripts/profile_blocked.py 32
-PROBE_C=16383 PROBE_PIVOTS=4 PROBE_MODES=p2p cap shard_pick_r2 "k_shard_pick<\(bool\)1, \(bool\)0>|k_shard_pickILb1ELb0" 2 python scripts/probe_shard_pick.py
+# (one shard driven alone; the fused decision kernel of the rank-1 loop is the first k_shard_pick launches of the probe)
+PROBE_C=16383 PROBE_PIVOTS=4 PROBE_MODES=p2p cap shard_pick_r2 k_shard_pick 2 python scripts/probe_shard_pick.py
 ls -la $O /tmp/*.ncu-rep
