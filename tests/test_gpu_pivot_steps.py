@@ -30,6 +30,24 @@ def test_pivot_steps_equal_full_tableau_oracle_on_reference_fixtures(oracle, gol
             assert abs(js["optimalValue"] - g["z"]) <= 1e-9 * max(1.0, abs(g["z"])), name
 
 
+def test_wyndor_pivot_steps_are_the_published_iterations():
+    """The GPU's `pivotSteps` for the Wyndor LP of the reference's tests (tests/test_visualization_integration.py:38-48)
+    against the iterations printed in textbooks (Hillier & Lieberman), not against anything in this repo: the same
+    arrays pin the CPU oracle in tests/test_oracle_textbook.py."""
+    A = np.array([[1.0, 0.0], [0.0, 2.0], [3.0, 2.0]])
+    js = run_pivot_steps(A, np.array([4.0, 12.0, 18.0]), np.array([3.0, 5.0]), np.zeros(3, dtype=np.int8), True)
+    published = [
+        np.array([[1, 0, 1, 0, 0, 4], [0, 2, 0, 1, 0, 12], [3, 2, 0, 0, 1, 18], [-3, -5, 0, 0, 0, 0]], dtype=float),
+        np.array([[1, 0, 1, 0, 0, 4], [0, 1, 0, 0.5, 0, 6], [3, 0, 0, -1, 1, 6], [-3, 0, 0, 2.5, 0, 30]], dtype=float),
+        np.array([[0, 0, 1, 1 / 3, -1 / 3, 2], [0, 1, 0, 0.5, 0, 6], [1, 0, 0, -1 / 3, 1 / 3, 2], [0, 0, 0, 1.5, 1, 36]]),
+    ]
+    pivots = [(None, None), (1, 1), (2, 0)]
+    assert len(js["pivotSteps"]) == 3 and js["status"] == 0 and js["optimalValue"] == 36.0
+    for step, want, (wr, wc) in zip(js["pivotSteps"], published, pivots):
+        assert (step["pivotRowIndex"], step["pivotColIndex"]) == (wr, wc)
+        np.testing.assert_allclose(np.array(step["tableau"], dtype=float), want, rtol=0, atol=1e-14)
+
+
 def test_pivot_steps_equal_full_tableau_oracle_on_mixed_and_fuzz(oracle, golden):
     for k, g in enumerate(golden["mixed"]):
         A = np.array(g["A"], dtype=np.float64).reshape(len(g["b"]), len(g["c"]))
