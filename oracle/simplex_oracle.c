@@ -20,6 +20,8 @@
  * tests/golden/reference_golden.json; checked by tests/test_oracle_golden.py).  The PIVOT SEQUENCE and tableau entries are
  * "parity unpinned": no reference test or fixture holds a single tableau cell or pivot index
  * (SURVEY.md F4), so for those this file is the definition the CUDA path is compared with bit-for-bit.
+ * What anchors the iterations outside this repo: the Wyndor LP of the reference's tests reproduces the tableaux printed
+ * in textbooks cell for cell, and a two-phase LP with <=, = and >= rows its printed optimum (tests/test_oracle_textbook.py).
  *
  * Arithmetic contract shared with the CUDA kernels (DESIGN.md "Arithmetic contract"):
  *   p = T[r][s]; inv_p = 1/p; col_i = T[i][s];
